@@ -1,0 +1,50 @@
+"""arvae_b200 -- AR-VAE's attribute-regularization hot path, hand-written CUDA for NVIDIA B200.
+
+Drop-in replacements for the reference's ``Trainer.compute_reg_loss`` / ``reg_loss_sign`` /
+``compute_kld_loss`` and ``MnistVAE.reparametrize``, plus fused multi-dim and whole-head
+forms, on top of the C ABI in ``include/arvae_b200.h`` (``csrc/libarvae_b200.so``).
+"""
+from __future__ import annotations
+
+from . import _lib  # noqa: F401
+from .ops import (ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, compute_kld_loss, compute_reg_loss, latent_head,
+                  reg_loss_fused, reg_loss_rows, reg_loss_sign, reparam_kld_reg, reparametrize, sign_matrix)
+
+__version__ = "0.1.0"
+
+__all__ = ["compute_reg_loss", "reg_loss_sign", "reg_loss_fused", "reg_loss_rows", "compute_kld_loss",
+           "reparametrize", "latent_head", "reparam_kld_reg", "sign_matrix", "install", "uninstall",
+           "ALGO_AUTO", "ALGO_DENSE", "ALGO_SORTED"]
+
+_saved = {}
+
+
+def install(trainer_cls, vae_classes=()):
+    """Swap the hot path into the reference's classes with zero edits to its trainers.
+
+    ``trainer_cls`` is the reference's ``utils.trainer.Trainer``: its static methods
+    ``compute_reg_loss`` / ``reg_loss_sign`` / ``compute_kld_loss`` (utils/trainer.py:354-403) are
+    replaced, so ``ImageVAETrainer`` / ``MeasureVAETrainer.loss_and_acc_for_batch`` call the CUDA
+    path unchanged.  Each class in ``vae_classes`` (e.g. ``MnistVAE``, ``DspritesVAE``) gets the
+    fused ``reparametrize`` (imagevae/mnist_vae.py:74-87).
+    """
+    _saved[trainer_cls] = {n: trainer_cls.__dict__.get(n) for n in
+                           ("compute_reg_loss", "reg_loss_sign", "compute_kld_loss")}
+    trainer_cls.compute_reg_loss = staticmethod(compute_reg_loss)
+    trainer_cls.reg_loss_sign = staticmethod(reg_loss_sign)
+    trainer_cls.compute_kld_loss = staticmethod(compute_kld_loss)
+    for cls in vae_classes:
+        _saved[cls] = {"reparametrize": cls.__dict__.get("reparametrize")}
+        cls.reparametrize = lambda self, z_dist: reparametrize(z_dist)
+
+
+def uninstall():
+    """Undo :func:`install`."""
+    for cls, attrs in _saved.items():
+        for name, val in attrs.items():
+            if val is None:
+                if name in cls.__dict__:
+                    delattr(cls, name)
+            else:
+                setattr(cls, name, val)
+    _saved.clear()

@@ -1,0 +1,345 @@
+// api.cu -- the extern "C" surface of libarvae_b200.so (declared in include/arvae_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <cmath>
+
+#include "common.cuh"
+#include "reg_internal.cuh"
+
+namespace arvae {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};  // process-wide: autograd runs backward on its own thread
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail_cuda(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    (void)cudaGetLastError();
+    return (int)e;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- optional pair-kernel timing --------------------------------------------------------------
+constexpr int kProfRing = 64;
+struct Profiler {
+    bool on = false;
+    int n = 0;  // launches recorded since last read (may exceed the ring)
+    cudaEvent_t ev[kProfRing][2] = {};
+    bool made = false;
+};
+static thread_local Profiler g_prof;
+
+void profile_begin(cudaStream_t st) {
+    Profiler &P = g_prof;
+    if (!P.on) return;
+    if (!P.made) {
+        for (int i = 0; i < kProfRing; ++i) {
+            cudaEventCreate(&P.ev[i][0]);
+            cudaEventCreate(&P.ev[i][1]);
+        }
+        P.made = true;
+    }
+    cudaEventRecord(P.ev[P.n % kProfRing][0], st);
+}
+
+void profile_end(cudaStream_t st) {
+    Profiler &P = g_prof;
+    if (!P.on || !P.made) return;
+    cudaEventRecord(P.ev[P.n % kProfRing][1], st);
+    P.n++;
+}
+
+int sm_count() {
+    // immutable per-device cache (benign race: every thread computes the same value)
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+static int fill_dims(RegDims &d, const int32_t *reg_dims, const int32_t *label_cols, int R) {
+    if (R < 0 || R > ARVAE_MAX_REG_DIMS) {
+        set_error("R=%d out of range [0,%d]", R, ARVAE_MAX_REG_DIMS);
+        return ARVAE_E_BADARG;
+    }
+    if (R > 0 && !reg_dims) {
+        set_error("reg_dims is null");
+        return ARVAE_E_BADARG;
+    }
+    memset(&d, 0, sizeof(d));
+    for (int r = 0; r < R; ++r) {
+        d.zcol[r] = reg_dims[r];
+        d.lcol[r] = label_cols ? label_cols[r] : reg_dims[r];
+        if (d.zcol[r] < 0 || d.lcol[r] < 0) {
+            set_error("negative column index at r=%d (resolve python-style negatives before the call)", r);
+            return ARVAE_E_BADARG;
+        }
+    }
+    return 0;
+}
+
+// per-thread device buffers of the host-buffer entry point
+struct HostCache {
+    int dev = -1;
+    size_t z_bytes = 0, lab_bytes = 0, ws_bytes = 0, gc_bytes = 0;
+    float *z = nullptr, *lab = nullptr, *gz = nullptr, *gc = nullptr;
+    char *ws = nullptr;
+    double *loss = nullptr;
+    void release() {
+        cudaFree(z); cudaFree(lab); cudaFree(gz); cudaFree(gc); cudaFree(ws); cudaFree(loss);
+        z = lab = gz = gc = nullptr; ws = nullptr; loss = nullptr;
+        z_bytes = lab_bytes = ws_bytes = gc_bytes = 0;
+        dev = -1;
+    }
+};
+static thread_local HostCache g_host;
+
+}  // namespace arvae
+
+using namespace arvae;
+
+extern "C" {
+
+int arvae_version(void) { return ARVAE_VERSION; }
+
+const char *arvae_last_error(void) { return g_err; }
+
+void arvae_profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.n = 0;
+}
+
+int arvae_profile_pair_kernel_ms(float *sum_ms_out, int *n_out) {
+    Profiler &P = g_prof;
+    float sum = 0.f;
+    const int n = P.n < kProfRing ? P.n : kProfRing;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        ARVAE_CUDA_TRY(cudaEventSynchronize(P.ev[i][1]));
+        ARVAE_CUDA_TRY(cudaEventElapsedTime(&ms, P.ev[i][0], P.ev[i][1]));
+        sum += ms;
+    }
+    if (sum_ms_out) *sum_ms_out = sum;
+    if (n_out) *n_out = n;
+    P.n = 0;
+    return 0;
+}
+
+int64_t arvae_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int arvae_device_sm_count(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        fail_cuda(e, "cudaGetDevice");
+        return ARVAE_E_NODEVICE;
+    }
+    return sm_count();
+}
+
+size_t arvae_reg_loss_workspace_bytes(int64_t B_total, int64_t n_rows, int32_t R) {
+    if (B_total < 0 || n_rows < 0 || R < 0 || R > ARVAE_MAX_REG_DIMS) return 0;
+    return dense_layout(B_total, n_rows, R > 0 ? R : 1, sm_count()).bytes;
+}
+
+int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t z_col_stride,
+                              const float *labels_dev, int64_t lab_row_stride,
+                              int64_t lab_col_stride, const int32_t *reg_dims_host,
+                              const int32_t *label_cols_host, int32_t R, int64_t row_begin,
+                              int64_t row_end, int64_t B_total, float gamma, float factor,
+                              int32_t algo, double *loss_out_dev, float *loss_f32_out_dev,
+                              float *grad_cols_out_dev, double *row_loss_out_dev,
+                              void *workspace_dev, size_t workspace_bytes, void *stream) {
+    RegProblem P;
+    int rc = fill_dims(P.dims, reg_dims_host, label_cols_host, R);
+    if (rc) return rc;
+    if (B_total < 0 || row_begin < 0 || row_end < row_begin || row_end > B_total) {
+        set_error("bad row range [%lld,%lld) for B_total=%lld", (long long)row_begin,
+                  (long long)row_end, (long long)B_total);
+        return ARVAE_E_BADARG;
+    }
+    if (!loss_out_dev || !workspace_dev || (B_total > 0 && R > 0 && (!z_dev || !labels_dev))) {
+        set_error("null pointer argument");
+        return ARVAE_E_BADARG;
+    }
+    if (algo != ARVAE_ALGO_AUTO && algo != ARVAE_ALGO_DENSE && algo != ARVAE_ALGO_SORTED) {
+        set_error("unknown algo %d", algo);
+        return ARVAE_E_BADARG;
+    }
+    P.z = z_dev; P.zrs = z_row_stride; P.zcs = z_col_stride;
+    P.lab = labels_dev; P.lrs = lab_row_stride; P.lcs = lab_col_stride;
+    P.R = R; P.B = B_total; P.row_begin = row_begin; P.row_end = row_end;
+    P.gamma = gamma; P.factor = factor;
+    P.loss_out = loss_out_dev; P.loss_f32_out = loss_f32_out_dev; P.grad_cols_out = grad_cols_out_dev; P.row_loss_out = row_loss_out_dev;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    const DenseLayout L = dense_layout(B_total, row_end - row_begin, R > 0 ? R : 1, sm_count());
+    if (workspace_bytes < L.bytes) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, L.bytes);
+        return ARVAE_E_WORKSPACE;
+    }
+    if (R == 0) {  // empty dim tuple: the callers' loop adds nothing
+        ARVAE_CUDA_TRY(cudaMemsetAsync(loss_out_dev, 0, sizeof(double), st));
+        if (loss_f32_out_dev) ARVAE_CUDA_TRY(cudaMemsetAsync(loss_f32_out_dev, 0, sizeof(float), st));
+        return 0;
+    }
+    return run_reg_dense(P, L, reinterpret_cast<char *>(workspace_dev), st);
+}
+
+int arvae_reg_loss_scatter_bwd_f32(const float *grad_cols_dev, const float *grad_out_dev,
+                                   const int32_t *reg_dims_host, int32_t R, int64_t n_rows,
+                                   int64_t Z, float *grad_z_dev, int64_t gz_row_stride,
+                                   void *stream) {
+    RegDims d;
+    int rc = fill_dims(d, reg_dims_host, nullptr, R);
+    if (rc) return rc;
+    if (n_rows < 0 || Z < 0 || (n_rows * Z > 0 && (!grad_z_dev || (R > 0 && !grad_cols_dev)))) {
+        set_error("bad argument to scatter_bwd");
+        return ARVAE_E_BADARG;
+    }
+    for (int r = 0; r < R; ++r)
+        if (d.zcol[r] >= Z) {
+            set_error("reg dim %d out of range for Z=%lld", d.zcol[r], (long long)Z);
+            return ARVAE_E_BADARG;
+        }
+    return run_scatter_bwd(grad_cols_dev, grad_out_dev, d, R, n_rows, Z, grad_z_dev, gz_row_stride,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t arvae_latent_head_workspace_bytes(int64_t B, int64_t Z) {
+    if (B < 0 || Z < 0) return 0;
+    return latent_head_ws_bytes(B, Z);
+}
+
+int arvae_latent_head_fwd_f32(const float *loc_dev, const float *scale_dev, const float *eps_dev,
+                              int64_t B, int64_t Z, float beta, float capacity, float *z_out_dev,
+                              double *kld_sum_out_dev, float *kld_mean_out_dev,
+                              float *kld_loss_out_dev, float *kcoef_out_dev, void *ws_dev,
+                              size_t ws_bytes, void *stream) {
+    if (B < 0 || Z < 0 || !kld_sum_out_dev || !ws_dev ||
+        (B * Z > 0 && (!loc_dev || !scale_dev || !eps_dev || !z_out_dev))) {
+        set_error("bad argument to latent_head_fwd");
+        return ARVAE_E_BADARG;
+    }
+    return run_latent_head_fwd(loc_dev, scale_dev, eps_dev, B, Z, beta, capacity, z_out_dev,
+                               kld_sum_out_dev, kld_mean_out_dev, kld_loss_out_dev, kcoef_out_dev,
+                               ws_dev, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int arvae_latent_head_bwd_f32(const float *loc_dev, const float *scale_dev, const float *eps_dev,
+                              const float *dz_up_dev, const float *grad_cols_dev,
+                              const float *greg_dev, const int32_t *reg_dims_host, int32_t R,
+                              float kscale, const float *kcoef_dev, const float *gkld_dev,
+                              int64_t B, int64_t Z, float *dloc_dev, float *dscale_dev,
+                              void *stream) {
+    RegDims d;
+    int rc = fill_dims(d, reg_dims_host, nullptr, grad_cols_dev ? R : 0);
+    if (rc) return rc;
+    if (B < 0 || Z < 0 || (B * Z > 0 && (!loc_dev || !scale_dev || !eps_dev))) {
+        set_error("bad argument to latent_head_bwd");
+        return ARVAE_E_BADARG;
+    }
+    return run_latent_head_bwd(loc_dev, scale_dev, eps_dev, dz_up_dev, grad_cols_dev, greg_dev, d,
+                               grad_cols_dev ? R : 0, kscale, kcoef_dev, gkld_dev, B, Z, dloc_dev,
+                               dscale_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z, const float *labels_host,
+                            int64_t A, const int32_t *reg_dims_host,
+                            const int32_t *label_cols_host, int32_t R, float gamma, float factor,
+                            int32_t algo, float *loss_out_host, float *grad_z_out_host,
+                            void *stream) {
+    if (B < 0 || Z <= 0 || A <= 0 || !loss_out_host || (B > 0 && (!z_host || !labels_host))) {
+        set_error("bad argument to reg_loss_host");
+        return ARVAE_E_BADARG;
+    }
+    RegDims d;
+    int rc = fill_dims(d, reg_dims_host, label_cols_host, R);
+    if (rc) return rc;
+    for (int r = 0; r < R; ++r)
+        if (d.zcol[r] >= Z || d.lcol[r] >= A) {
+            set_error("column index out of range at r=%d", r);
+            return ARVAE_E_BADARG;
+        }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int dev = 0;
+    ARVAE_CUDA_TRY(cudaGetDevice(&dev));
+    HostCache &C = g_host;
+    if (C.dev != dev) C.release();
+    C.dev = dev;
+    const size_t zb = sizeof(float) * (size_t)(B > 0 ? B : 1) * Z;
+    const size_t lb = sizeof(float) * (size_t)(B > 0 ? B : 1) * A;
+    const size_t gb = sizeof(float) * (size_t)(B > 0 ? B : 1) * (R > 0 ? R : 1);
+    const size_t wb = arvae_reg_loss_workspace_bytes(B, B, R);
+    if (C.z_bytes < zb) {
+        cudaFree(C.z); cudaFree(C.gz);
+        ARVAE_CUDA_TRY(cudaMalloc(&C.z, zb));
+        ARVAE_CUDA_TRY(cudaMalloc(&C.gz, zb));
+        C.z_bytes = zb;
+    }
+    if (C.lab_bytes < lb) {
+        cudaFree(C.lab);
+        ARVAE_CUDA_TRY(cudaMalloc(&C.lab, lb));
+        C.lab_bytes = lb;
+    }
+    if (C.gc_bytes < gb) {
+        cudaFree(C.gc);
+        ARVAE_CUDA_TRY(cudaMalloc(&C.gc, gb));
+        C.gc_bytes = gb;
+    }
+    if (C.ws_bytes < wb) {
+        cudaFree(C.ws);
+        ARVAE_CUDA_TRY(cudaMalloc(&C.ws, wb));
+        C.ws_bytes = wb;
+    }
+    if (!C.loss) ARVAE_CUDA_TRY(cudaMalloc(&C.loss, sizeof(double)));
+
+    if (B > 0) {
+        ARVAE_CUDA_TRY(cudaMemcpyAsync(C.z, z_host, sizeof(float) * (size_t)B * Z, cudaMemcpyHostToDevice, st));
+        ARVAE_CUDA_TRY(cudaMemcpyAsync(C.lab, labels_host, sizeof(float) * (size_t)B * A, cudaMemcpyHostToDevice, st));
+    }
+    rc = arvae_reg_loss_fwdbwd_f32(C.z, Z, 1, C.lab, A, 1, reg_dims_host, label_cols_host, R, 0, B, B,
+                                   gamma, factor, algo, C.loss, nullptr, grad_z_out_host ? C.gc : nullptr,
+                                   nullptr, C.ws, C.ws_bytes, stream);
+    if (rc) return rc;
+    if (grad_z_out_host && B > 0) {
+        rc = arvae_reg_loss_scatter_bwd_f32(C.gc, nullptr, reg_dims_host, R, B, Z, C.gz, Z, stream);
+        if (rc) return rc;
+        ARVAE_CUDA_TRY(cudaMemcpyAsync(grad_z_out_host, C.gz, sizeof(float) * (size_t)B * Z, cudaMemcpyDeviceToHost, st));
+    }
+    double loss = 0.0;
+    ARVAE_CUDA_TRY(cudaMemcpyAsync(&loss, C.loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
+    *loss_out_host = (float)loss;
+    return 0;
+}
+
+void arvae_host_release(void) { g_host.release(); }
+
+int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
+                             int8_t *out_dev, void *stream) {
+    if (B < 0 || (B > 0 && (!labels_dev || !out_dev))) {
+        set_error("bad argument to sign_matrix");
+        return ARVAE_E_BADARG;
+    }
+    return run_sign_matrix(labels_dev, lab_stride, B, out_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// common.cuh -- shared helpers for libarvae_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/arvae_b200.h"
+
+namespace arvae {
+
+// ---- error plumbing (thread-local message, see arvae_last_error) -------------------------------
+void set_error(const char *fmt, ...);
+int fail_cuda(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+// pair-kernel timing hooks (no-ops unless arvae_profile_enable(1))
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
+
+#define ARVAE_CUDA_TRY(expr)                                        \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return ::arvae::fail_cuda(_e, #expr); \
+    } while (0)
+
+#define ARVAE_LAUNCH_CHECK(name)                                      \
+    do {                                                              \
+        ::arvae::count_launch();                                      \
+        cudaError_t _e = cudaGetLastError();                          \
+        if (_e != cudaSuccess) return ::arvae::fail_cuda(_e, name);   \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- device math ------------------------------------------------------------------------------
+// Single-instruction MUFU ops. The .ftz forms compile to one MUFU each (no range fix-up code);
+// flushing only affects |2^d| < 2^-126, where tanh is already saturated to +-1 in float.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// sign(a_i - a_j) exactly as torch.sign of the float difference: equals (a_i>a_j)-(a_i<a_j) for
+// every pair of floats including NaN, +-inf, +-0 and subnormals. Compiled
+// WITHOUT flush-to-zero so distinct subnormals compare unequal.
+__device__ __forceinline__ float pair_sign(float ai, float aj) {
+    return (ai > aj ? 1.0f : 0.0f) - (ai < aj ? 1.0f : 0.0f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Column padding: (u = +inf, a = NaN) makes a padded column contribute exactly |t - s| = 1 and
+// gradient 0 to every row (2^-inf = 0 -> r = 1 -> t = -1; NaN compares false -> s = 0), so the
+// pair loops need no bounds checks and the host subtracts n_pad per row.
+#define ARVAE_PAD_U (__int_as_float(0x7f800000))
+#define ARVAE_PAD_A (__int_as_float(0x7fc00000))
+
+}  // namespace arvae

@@ -1,0 +1,389 @@
+"""Torch-facing operators for AR-VAE's attribute-regularization hot path.
+
+Mirrors the reference's static methods (same names, argument order, defaults,
+return dtype and error behaviour) on top of the C ABI in
+``include/arvae_b200.h``:
+
+===========================================  ==========================================
+reference (/root/reference)                   here
+===========================================  ==========================================
+utils/trainer.py:369  compute_reg_loss        :func:`compute_reg_loss` (also tuple dims)
+utils/trainer.py:378  reg_loss_sign           :func:`reg_loss_sign`
+utils/trainer.py:354  compute_kld_loss        :func:`compute_kld_loss`
+imagevae/mnist_vae.py:74  reparametrize       :func:`reparametrize`
+trainers' per-dim loop (image_vae_trainer.py  :func:`reg_loss_fused`
+ :171-180, measure_vae_trainer.py:131-142)
+reparametrize + KLD + loop, one autograd node  :func:`reparam_kld_reg`
+===========================================  ==========================================
+
+CUDA float32 only on the latent side; there is no CPU / PyTorch fallback --
+non-CUDA inputs raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib
+
+ALGO_AUTO, ALGO_DENSE, ALGO_SORTED = _lib.ALGO_AUTO, _lib.ALGO_DENSE, _lib.ALGO_SORTED
+
+_EXACT_IN_F32 = (torch.float32, torch.float16, torch.bfloat16, torch.int8, torch.uint8, torch.int16,
+                 torch.bool)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"arvae_b200: {name} must be a CUDA tensor (no CPU fallback exists for this path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"arvae_b200: {name} must be float32, got {t.dtype}")
+
+
+def _scalar(v) -> float:
+    """gamma / factor / beta / capacity may be python numbers or 0-d / 1-element tensors."""
+    if isinstance(v, torch.Tensor):
+        return float(v.detach().reshape(-1)[0].item()) if v.numel() == 1 else float(v)
+    return float(v)
+
+
+def _rank_labels(col: torch.Tensor) -> torch.Tensor:
+    """Dense ranks as float32 for label dtypes whose float32 cast is not injective (int32/int64/
+    float64).  sign(rank_i - rank_j) == sign(a_i - a_j) in the label's own dtype, which is how
+    the reference takes it (utils/trainer.py:395,400); NaN stays NaN (ties with everything)."""
+    if col.is_floating_point():
+        nan = torch.isnan(col)
+        filled = torch.where(nan, torch.zeros_like(col), col)
+        ranks = torch.unique(filled, sorted=True, return_inverse=True)[1].to(torch.float32)
+        return torch.where(nan, torch.full_like(ranks, float("nan")), ranks)
+    return torch.unique(col, sorted=True, return_inverse=True)[1].to(torch.float32)
+
+
+def _prepare_labels(labels: torch.Tensor, label_cols: Sequence[int], B: int, device) -> Tuple[torch.Tensor, Tuple[int, ...]]:
+    """Return a float32 CUDA [B, A'] tensor (any strides, never copied when already float32) and
+    the label-column index per regularised dim."""
+    if not isinstance(labels, torch.Tensor):
+        raise TypeError(f"labels must be a torch.Tensor, got {type(labels).__name__}")
+    if not labels.is_cuda:
+        raise RuntimeError("arvae_b200: labels must be a CUDA tensor (no CPU fallback exists for this path)")
+    if labels.device != device:
+        raise RuntimeError(f"arvae_b200: labels on {labels.device}, latent on {device}")
+    if labels.dim() == 1:
+        labels = labels.unsqueeze(1)
+    if labels.dim() != 2:
+        raise RuntimeError(f"arvae_b200: labels must be 1-D or 2-D, got shape {tuple(labels.shape)}")
+    if labels.shape[0] != B:
+        # the reference fails in the subtraction of mismatched distance matrices (RuntimeError)
+        raise RuntimeError(f"The size of tensor a ({B * B}) must match the size of tensor b "
+                           f"({labels.shape[0] * labels.shape[0]}) at non-singleton dimension 0")
+    A = labels.shape[1]
+    cols = []
+    for c in label_cols:
+        c = int(c)
+        if c < -A or c >= A:
+            raise IndexError(f"index {c} is out of bounds for dimension 1 with size {A}")
+        cols.append(c % A)
+    if labels.dtype == torch.float32:
+        return labels.detach(), tuple(cols)
+    if labels.dtype in _EXACT_IN_F32:
+        return labels.detach().to(torch.float32), tuple(cols)
+    ranked = torch.stack([_rank_labels(labels.detach()[:, c]) for c in cols], dim=1)
+    return ranked, tuple(range(len(cols)))
+
+
+def _launch_reg(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], label_cols: Sequence[int],
+                gamma: float, factor: float, row_begin: int, row_end: int, want_grad: bool, algo: int,
+                want_row_loss: bool = False):
+    """One call of arvae_reg_loss_fwdbwd_f32. Returns (loss64[()] , loss32[()], grad_cols|None, row_loss|None)."""
+    lib = _lib.load()
+    dev = z.device
+    B = z.shape[0]
+    R = len(reg_dims)
+    n_rows = row_end - row_begin
+    with torch.cuda.device(dev):
+        loss64 = torch.empty((), dtype=torch.float64, device=dev)
+        loss32 = torch.empty((), dtype=torch.float32, device=dev)
+        grad_cols = torch.empty((n_rows, R), dtype=torch.float32, device=dev) if want_grad else None
+        row_loss = torch.empty((n_rows, R), dtype=torch.float64, device=dev) if want_row_loss else None
+        ws_bytes = int(lib.arvae_reg_loss_workspace_bytes(B, n_rows, R))
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        rc = lib.arvae_reg_loss_fwdbwd_f32(
+            _ptr(z), z.stride(0), z.stride(1), _ptr(labels), labels.stride(0), labels.stride(1),
+            _lib.i32_array(reg_dims), _lib.i32_array(label_cols), R, row_begin, row_end, B,
+            gamma, factor, algo, _ptr(loss64), _ptr(loss32), _ptr(grad_cols), _ptr(row_loss),
+            _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(rc, "arvae_reg_loss_fwdbwd_f32")
+    return loss64, loss32, grad_cols, row_loss
+
+
+def _scatter_bwd(grad_cols: torch.Tensor, grad_out: Optional[torch.Tensor], reg_dims: Sequence[int],
+                 n_rows: int, Z: int) -> torch.Tensor:
+    lib = _lib.load()
+    dev = grad_cols.device
+    with torch.cuda.device(dev):
+        grad_z = torch.empty((n_rows, Z), dtype=torch.float32, device=dev)
+        if grad_out is not None:
+            grad_out = grad_out.detach().to(torch.float32).contiguous()
+        rc = lib.arvae_reg_loss_scatter_bwd_f32(_ptr(grad_cols), _ptr(grad_out), _lib.i32_array(reg_dims),
+                                                len(reg_dims), n_rows, Z, _ptr(grad_z), Z, _stream(dev))
+        _lib.check(rc, "arvae_reg_loss_scatter_bwd_f32")
+    return grad_z
+
+
+class _RegLossFn(torch.autograd.Function):
+    """loss = sum_r gamma * mean_ij |tanh(factor (z_i,r - z_j,r)) - sign(a_i,r - a_j,r)| with the
+    gradient produced in the same pass (row sums)."""
+
+    @staticmethod
+    def forward(ctx, z, labels, reg_dims, label_cols, gamma, factor, algo):
+        want_grad = bool(ctx.needs_input_grad[0])
+        _, loss32, grad_cols, _ = _launch_reg(z.detach(), labels, reg_dims, label_cols, gamma, factor,
+                                              0, z.shape[0], want_grad, algo)
+        ctx.reg_dims = tuple(reg_dims)
+        ctx.shape = tuple(z.shape)
+        if want_grad:
+            ctx.save_for_backward(grad_cols)
+        return loss32
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (grad_cols,) = ctx.saved_tensors
+        B, Z = ctx.shape
+        return _scatter_bwd(grad_cols, grad_out, ctx.reg_dims, B, Z), None, None, None, None, None, None
+
+
+def _normalize_dims(reg_dims: Sequence[int], Z: int) -> Tuple[int, ...]:
+    out = []
+    for d in reg_dims:
+        d = int(d)
+        if d < -Z or d >= Z:
+            raise IndexError(f"index {d} is out of bounds for dimension 1 with size {Z}")
+        out.append(d % Z)
+    if len(out) > _lib.MAX_REG_DIMS:
+        raise RuntimeError(f"arvae_b200: at most {_lib.MAX_REG_DIMS} regularised dims per call")
+    return tuple(out)
+
+
+def reg_loss_fused(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], gamma, factor=1.0,
+                   label_cols: Optional[Sequence[int]] = None, algo: int = ALGO_AUTO) -> torch.Tensor:
+    """All regularised dims in one launch: the value the trainers' loop accumulates
+    (imagevae/image_vae_trainer.py:171-180), ``sum_dim compute_reg_loss(z, labels[:, dim], dim, gamma, factor)``.
+
+    ``labels`` is the [B, A] attribute matrix; label column ``dim`` pairs with latent ``dim``
+    unless ``label_cols`` says otherwise.  Returns a 0-d float32 tensor, differentiable w.r.t. ``z``.
+    """
+    _require_cuda_f32(z, "z")
+    if z.dim() != 2:
+        raise RuntimeError(f"arvae_b200: z must be [B, Z], got shape {tuple(z.shape)}")
+    dims = _normalize_dims(reg_dims, z.shape[1])
+    lab, lcols = _prepare_labels(labels, dims if label_cols is None else label_cols, z.shape[0], z.device)
+    if len(lcols) != len(dims):
+        raise RuntimeError("arvae_b200: label_cols and reg_dims differ in length")
+    return _RegLossFn.apply(z, lab, dims, lcols, _scalar(gamma), _scalar(factor), int(algo))
+
+
+def compute_reg_loss(z: torch.Tensor, labels: torch.Tensor, reg_dim: Union[int, Sequence[int]], gamma,
+                     factor=1.0) -> torch.Tensor:
+    """Drop-in for ``Trainer.compute_reg_loss`` (utils/trainer.py:369-376).
+
+    ``reg_dim`` int (negative allowed): ``labels`` is the [B] attribute vector, usually the strided
+    view ``labels[:, dim]`` -- consumed in place, no copy.  ``reg_dim`` tuple (extension): ``labels``
+    is the [B, A] matrix and the result is the sum over the dims.
+    """
+    if isinstance(reg_dim, (tuple, list)):
+        return reg_loss_fused(z, labels, tuple(reg_dim), gamma, factor)
+    _require_cuda_f32(z, "z")
+    if z.dim() != 2:
+        raise RuntimeError(f"arvae_b200: z must be [B, Z], got shape {tuple(z.shape)}")
+    if isinstance(labels, torch.Tensor) and labels.dim() != 1:
+        labels = labels.reshape(-1)  # the reference flattens with view(-1, 1)
+    dims = _normalize_dims((reg_dim,), z.shape[1])
+    lab, lcols = _prepare_labels(labels, (0,), z.shape[0], z.device)
+    return _RegLossFn.apply(z, lab, dims, lcols, _scalar(gamma), _scalar(factor), ALGO_AUTO)
+
+
+def reg_loss_sign(latent_code: torch.Tensor, attribute: torch.Tensor, factor=1.0) -> torch.Tensor:
+    """Drop-in for ``Trainer.reg_loss_sign`` (utils/trainer.py:378-403): both arguments are [N]."""
+    _require_cuda_f32(latent_code, "latent_code")
+    x = latent_code.reshape(-1, 1)
+    lab, lcols = _prepare_labels(attribute.reshape(-1), (0,), x.shape[0], x.device)
+    return _RegLossFn.apply(x, lab, (0,), lcols, 1.0, _scalar(factor), ALGO_AUTO)
+
+
+def reg_loss_rows(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], gamma, factor, row_begin: int,
+                  row_end: int, want_grad: bool = True, algo: int = ALGO_AUTO, want_row_loss: bool = False):
+    """Row-block form (no autograd): the block's share of the loss as a 0-d float64 tensor, the
+    gradient columns [rows, R] and optionally the per-row loss sums [rows, R]."""
+    _require_cuda_f32(z, "z")
+    dims = _normalize_dims(reg_dims, z.shape[1])
+    lab, lcols = _prepare_labels(labels, dims, z.shape[0], z.device)
+    loss64, _, grad_cols, row_loss = _launch_reg(z.detach(), lab, dims, lcols, _scalar(gamma), _scalar(factor),
+                                                 int(row_begin), int(row_end), want_grad, int(algo),
+                                                 want_row_loss)
+    return loss64, grad_cols, row_loss
+
+
+def sign_matrix(attribute: torch.Tensor) -> torch.Tensor:
+    """int8 [B,B] sign(a_i - a_j) from the same compare the pair kernels use (parity tests)."""
+    lab, _ = _prepare_labels(attribute.reshape(-1), (0,), attribute.numel(), attribute.device)
+    B = lab.shape[0]
+    out = torch.empty((B, B), dtype=torch.int8, device=lab.device)
+    with torch.cuda.device(lab.device):
+        rc = _lib.load().arvae_reg_sign_matrix_i8(_ptr(lab), lab.stride(0), B, _ptr(out), _stream(lab.device))
+        _lib.check(rc, "arvae_reg_sign_matrix_i8")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# latent head: reparametrize + KLD
+# --------------------------------------------------------------------------------------------
+def _head_fwd(loc, scale, eps, beta: float, capacity: float):
+    lib = _lib.load()
+    dev = loc.device
+    B, Z = loc.shape
+    with torch.cuda.device(dev):
+        z = torch.empty((B, Z), dtype=torch.float32, device=dev)
+        kld_sum = torch.empty((), dtype=torch.float64, device=dev)
+        kld_mean = torch.empty((), dtype=torch.float32, device=dev)
+        kld_loss = torch.empty((), dtype=torch.float32, device=dev)
+        kcoef = torch.empty((), dtype=torch.float32, device=dev)
+        ws_bytes = int(lib.arvae_latent_head_workspace_bytes(B, Z))
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        rc = lib.arvae_latent_head_fwd_f32(_ptr(loc), _ptr(scale), _ptr(eps), B, Z, beta, capacity, _ptr(z),
+                                           _ptr(kld_sum), _ptr(kld_mean), _ptr(kld_loss), _ptr(kcoef),
+                                           _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(rc, "arvae_latent_head_fwd_f32")
+    return z, kld_sum, kld_mean, kld_loss, kcoef
+
+
+def _head_bwd(loc, scale, eps, dz_up, grad_cols, greg, reg_dims, kscale: float, kcoef, gkld, need_loc=True,
+              need_scale=True):
+    lib = _lib.load()
+    dev = loc.device
+    B, Z = loc.shape
+    with torch.cuda.device(dev):
+        dloc = torch.empty((B, Z), dtype=torch.float32, device=dev) if need_loc else None
+        dscale = torch.empty((B, Z), dtype=torch.float32, device=dev) if need_scale else None
+        rc = lib.arvae_latent_head_bwd_f32(_ptr(loc), _ptr(scale), _ptr(eps), _ptr(dz_up), _ptr(grad_cols),
+                                           _ptr(greg), _lib.i32_array(reg_dims), len(reg_dims), kscale,
+                                           _ptr(kcoef), _ptr(gkld), B, Z, _ptr(dloc), _ptr(dscale),
+                                           _stream(dev))
+        _lib.check(rc, "arvae_latent_head_bwd_f32")
+    return dloc, dscale
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+class _LatentHeadFn(torch.autograd.Function):
+    """(loc, scale, eps) -> (z = loc + eps*scale, kld_mean = mean_b sum_d KL(N(loc,scale) || N(0,1)))."""
+
+    @staticmethod
+    def forward(ctx, loc, scale, eps):
+        z, _, kld_mean, _, _ = _head_fwd(loc, scale, eps, 1.0, 0.0)
+        ctx.save_for_backward(loc, scale, eps)
+        return z, kld_mean
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dz, dkld):
+        loc, scale, eps = ctx.saved_tensors
+        dloc, dscale = _head_bwd(loc, scale, eps, _f32c(dz), None, None, (), 1.0 / max(loc.shape[0], 1), None,
+                                 _f32c(dkld), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dloc, dscale, None
+
+
+class _HeadRegFn(torch.autograd.Function):
+    """Whole latent-loss head in one node: reparametrize + KLD loss + attribute-regularization loss."""
+
+    @staticmethod
+    def forward(ctx, loc, scale, eps, labels, reg_dims, label_cols, beta, capacity, gamma, factor, algo):
+        z, _, _, kld_loss, kcoef = _head_fwd(loc, scale, eps, beta, capacity)
+        want_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        _, reg32, grad_cols, _ = _launch_reg(z, labels, reg_dims, label_cols, gamma, factor, 0, z.shape[0],
+                                             want_grad, algo)
+        ctx.reg_dims = tuple(reg_dims)
+        ctx.save_for_backward(loc, scale, eps, grad_cols if want_grad else None, kcoef)
+        return z, kld_loss, reg32
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dz, dkld, dreg):
+        loc, scale, eps, grad_cols, kcoef = ctx.saved_tensors
+        dloc, dscale = _head_bwd(loc, scale, eps, _f32c(dz), grad_cols, _f32c(dreg), ctx.reg_dims, 1.0,
+                                 kcoef, _f32c(dkld), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return (dloc, dscale) + (None,) * 9
+
+
+def _check_head_inputs(loc, scale, eps):
+    for t, n in ((loc, "loc"), (scale, "scale"), (eps, "eps")):
+        _require_cuda_f32(t, n)
+    if loc.dim() != 2 or scale.shape != loc.shape or eps.shape != loc.shape:
+        raise RuntimeError("arvae_b200: loc, scale and eps must be [B, Z] tensors of one shape")
+    return loc.contiguous(), scale.contiguous(), eps.detach().contiguous()
+
+
+def latent_head(loc: torch.Tensor, scale: torch.Tensor, eps: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``z_tilde`` and the batch-mean KL divergence to the unit prior, fused; differentiable
+    w.r.t. ``loc`` and ``scale`` (imagevae/mnist_vae.py:79, utils/trainer.py:364-365)."""
+    loc, scale, eps = _check_head_inputs(loc, scale, eps)
+    return _LatentHeadFn.apply(loc, scale, eps)
+
+
+def reparam_kld_reg(loc: torch.Tensor, scale: torch.Tensor, eps: torch.Tensor, labels: torch.Tensor,
+                    reg_dims: Sequence[int], beta, capacity, gamma, factor=1.0,
+                    label_cols: Optional[Sequence[int]] = None, algo: int = ALGO_AUTO
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fused latent-loss head: returns ``(z_tilde, kld_loss, reg_loss)`` where
+
+    * ``z_tilde = loc + eps * scale``                                   (mnist_vae.py:79)
+    * ``kld_loss = beta * |mean_b sum_d KL - capacity|``                (trainer.py:354-367)
+    * ``reg_loss = sum_dim gamma * reg_loss_sign(z_tilde[:, dim], labels[:, dim], factor)``
+      (trainer.py:369-403 through the trainers' loop)
+
+    One autograd node; its backward is a single pass over [B, Z] that folds the decoder's
+    ``dz``, the regularization gradient and the KLD gradient into ``dloc`` and ``dscale``.
+    """
+    loc, scale, eps = _check_head_inputs(loc, scale, eps)
+    dims = _normalize_dims(reg_dims, loc.shape[1])
+    lab, lcols = _prepare_labels(labels, dims if label_cols is None else label_cols, loc.shape[0], loc.device)
+    return _HeadRegFn.apply(loc, scale, eps, lab, dims, lcols, _scalar(beta), _scalar(capacity), _scalar(gamma),
+                            _scalar(factor), int(algo))
+
+
+def reparametrize(z_dist: torch.distributions.Normal):
+    """Drop-in for ``MnistVAE.reparametrize`` (imagevae/mnist_vae.py:74-87): same RNG draw order
+    (noise for z_tilde first, then the unused prior sample).  The KL term is computed in the same
+    pass and parked on the returned prior so that :func:`compute_kld_loss` can pick it up."""
+    loc, scale = z_dist.loc, z_dist.scale
+    eps = torch.distributions.utils._standard_normal(loc.shape, dtype=loc.dtype, device=loc.device)
+    z_tilde, kld_mean = latent_head(loc, scale, eps)
+    prior_dist = torch.distributions.Normal(loc=torch.zeros_like(loc), scale=torch.ones_like(scale))
+    z_prior = prior_dist.sample()
+    prior_dist._arvae_kld_mean = kld_mean
+    prior_dist._arvae_kld_of = z_dist
+    return z_tilde, z_prior, prior_dist
+
+
+def compute_kld_loss(z_dist, prior_dist, beta, c=0.0) -> torch.Tensor:
+    """Drop-in for ``Trainer.compute_kld_loss`` (utils/trainer.py:354-367) for a diagonal Normal
+    against the unit prior: ``beta * |kld - c|`` with ``kld`` from the fused head when
+    :func:`reparametrize` produced ``prior_dist``, else computed by the head kernel now."""
+    kld = getattr(prior_dist, "_arvae_kld_mean", None)
+    if kld is None or getattr(prior_dist, "_arvae_kld_of", None) is not z_dist:
+        loc, scale = z_dist.loc, z_dist.scale
+        _, kld = latent_head(loc, scale, torch.zeros_like(loc))
+    return beta * (kld - c).abs()

@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the attribute-regularization hot path on B200.
+
+Metric (BASELINE.json): fused reg-loss forward+backward throughput in Gpairs/s, pairs = B^2 * R
+ordered pairs per step, on the "MnistRESNET large-batch" config C4 (B=65536, Z=16, R=6, gamma=10,
+delta=1), synthetic Morpho-MNIST-shaped labels.  A step is one complete op: pack + pair kernel +
+epilogue + gradient scatter (loss and dL/dz both produced).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+N>1 is strong scaling of the same global batch: each rank owns B/N rows (its own samples), the
+packed columns are all-gathered over NCCL, each rank sweeps its rows against all columns and one
+float64 loss partial is all-reduced (arvae_b200/distributed.py).
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = "c4_mnist_b65536"
+MUFU_LANES_PER_CLK_SM = 16.0     # sm_100 MUFU issue rate; confirmed by bench_tools/pipe_rates.cu (profiles/)
+MUFU_PER_PAIR = 2.0              # EX2 + RCP: cheapest tanh that meets the 1e-5 gate
+ALGO_BYTES_PER_ROWCOL = 4        # float32 per latent / label / gradient element
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], [], [], set()
+        for t, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            inside = (t0 - 0.05) <= t <= (t1 + 0.15)
+            try:
+                if inside:
+                    sm.append(float(parts[1]))
+                    power.append(float(parts[3]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            if inside:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than one sample: use everything we saw
+            for t, line in self.rows:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's torch-CPU op chain (oracle/torch_port.py) on a bounded row sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(case, target_seconds: float, steps: int = 1, warmup: int = 0):
+    """Times forward+backward of the reference op chain on rows [0, n) x all B columns x R dims.
+    Returns (Gpairs/s, dict describing the sample)."""
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    z, labels = case["z"], case["labels"]
+    B, R = case["B"], len(case["reg_dims"])
+
+    def run(n_rows):
+        t = time.perf_counter()
+        torch_port.reg_loss_dims_rows_fwdbwd(z, labels, case["reg_dims"], case["gamma"], case["delta"], (0, n_rows))
+        return time.perf_counter() - t
+
+    n = min(64, B)
+    run(n)                       # touch pages, spin up the thread pool
+    dt = run(n)
+    rate = n * B * R / max(dt, 1e-9)
+    # grow the sample toward the time target; cap by memory (~10 live [n, B] float32 temporaries)
+    mem_cap = max(64, int(24e9 / (B * 4 * 12)))
+    n = int(min(B, mem_cap, max(n, rate * target_seconds / (B * R))))
+    for _ in range(warmup):
+        run(n)
+    times = [run(n) for _ in range(max(1, steps))]
+    dt = statistics.median(times)
+    pairs = float(n) * B * R
+    return pairs / dt / 1e9, {
+        "cores": threads, "kind": "port",
+        "sample": f"rows [0,{n}) x all {B} columns x {R} dims of {WORKLOAD} ({pairs/1e9:.3f} Gpairs per step, "
+                  f"{len(times)} steps, median {dt:.2f} s); torch {torch.__version__} CPU op chain of "
+                  f"oracle/torch_port.py (= reference utils/trainer.py:378-403 + autograd), {threads} threads",
+        "ms_per_step": dt * 1e3,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from arvae_b200 import synth
+    case = synth.make_case(WORKLOAD)
+    B, R = case["B"], len(case["reg_dims"])
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    value, info = cpu_reference_sample(case, min(20.0, budget), steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "reg_loss_fwd_bwd_throughput", "value": value, "unit": "Gpairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "B": B, "Z": case["Z"], "R": R, "gamma": case["gamma"],
+                   "delta": case["delta"], "pairs_per_step": float(B) * B * R},
+        "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"]},
+        "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 dense, 2 sorted")
+    ap.add_argument("--batch", type=int, default=0, help="override B (parity/scaling sweeps; 0 = config C4)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    import arvae_b200
+    from arvae_b200 import _lib, synth
+    from arvae_b200 import distributed as adist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    case = synth.make_case(WORKLOAD, args.batch or None)
+    B, Z, R = case["B"], case["Z"], len(case["reg_dims"])
+    A = case["labels"].shape[1]
+    dims = case["reg_dims"]
+    gamma, delta = case["gamma"], case["delta"]
+    assert B % world == 0
+    n_local = B // world
+    r0 = rank * n_local
+    pairs = float(B) * B * R
+
+    z_host = case["z"][r0:r0 + n_local].contiguous().pin_memory()
+    lab_host = case["labels"][r0:r0 + n_local].contiguous().pin_memory()
+    z_dev = z_host.to(dev)
+    lab_dev = lab_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        """One step with inputs resident in HBM: loss + dL/dz for this rank's rows."""
+        z = z_dev.detach().requires_grad_(True)
+        if world == 1:
+            loss = arvae_b200.reg_loss_fused(z, lab_dev, dims, gamma, delta, algo=args.algo)
+        else:
+            loss = adist.reg_loss_sharded(z, lab_dev, dims, gamma, delta, algo=args.algo)
+        loss.backward()
+        return loss, z.grad
+
+    grad_host = torch.empty((n_local, Z), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        """The same step through the public API with HOST buffers: H2D of this step's inputs from pinned
+        memory, the op, D2H of the loss and the gradient."""
+        if world == 1:
+            loss_c = ctypes.c_float()
+            rc = lib.arvae_reg_loss_host_f32(ctypes.c_void_p(z_host.data_ptr()), n_local, Z,
+                                             ctypes.c_void_p(lab_host.data_ptr()), A, _lib.i32_array(dims),
+                                             _lib.i32_array(dims), R, gamma, delta, args.algo, ctypes.byref(loss_c),
+                                             ctypes.c_void_p(grad_host.data_ptr()),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.check(rc, "arvae_reg_loss_host_f32")
+            return loss_c.value
+        z = z_host.to(dev, non_blocking=True).requires_grad_(True)
+        lab = lab_host.to(dev, non_blocking=True)
+        loss = adist.reg_loss_sharded(z, lab, dims, gamma, delta, algo=args.algo)
+        loss.backward()
+        grad_host.copy_(z.grad, non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, do_flush):
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        ev0.record()
+        out = None
+        for _ in range(steps):
+            if do_flush:
+                flush.zero_()
+            out = fn()
+        ev1.record()
+        barrier()
+        t1 = time.time()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out, t0, t1
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    for _ in range(3):
+        step_e2e()
+    barrier()
+
+    # ---- device-resident timing (value), with the pair kernel timed alone through the library hooks
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lib.arvae_launch_count(1)
+    lib.arvae_profile_enable(1)
+    ms_total, out, t0, t1 = timed(step_device, args.steps, True)
+    ksum, kn = ctypes.c_float(), ctypes.c_int()
+    lib.arvae_profile_pair_kernel_ms(ctypes.byref(ksum), ctypes.byref(kn))
+    lib.arvae_profile_enable(0)
+    launches = int(lib.arvae_launch_count(1))
+    loss_val = float(out[0].item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = pairs / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end timing (host buffers in, host results out) -----------------------------------
+    ms_e2e_total, loss_e2e, _, _ = timed(step_e2e, args.steps, True)
+    ms_e2e = ms_e2e_total / args.steps
+    e2e_value = pairs / (ms_e2e * 1e-3) / 1e9
+    h2d = z_host.numel() * 4 + lab_host.numel() * 4
+    d2h = grad_host.numel() * 4 + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (pair) kernel -----------------------------------------------------
+    peaks, peaks_src = load_peaks()
+    sm_count = lib.arvae_device_sm_count()
+    f_ghz = float(peaks.get("sm_max_mhz", 1965.0)) / 1e3
+    mufu_peak = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / MUFU_PER_PAIR  # Gpairs/s per GPU
+    k_ms = (ksum.value / kn.value) if kn.value else ms_step
+    pairs_per_launch = pairs / world  # this rank's rows x all columns x R
+    achieved = pairs_per_launch / (k_ms * 1e-3) / 1e9
+    algo_bytes = (2 * B * R + n_local * R) * ALGO_BYTES_PER_ROWCOL  # columns in (u, a) + gradient columns out
+    roofline = {
+        "bound": "mufu", "achieved": achieved, "peak": mufu_peak, "unit": "Gpairs/s", "frac": achieved / mufu_peak,
+        "traffic": None,
+        "peak_source": f"{MUFU_LANES_PER_CLK_SM:.0f} MUFU lanes/clk/SM x {sm_count} SMs x {f_ghz:.3f} GHz (sm_max_mhz, "
+                       f"MEASURED_PEAKS.json {peaks_src}) / {MUFU_PER_PAIR:.0f} MUFU per evaluated pair; "
+                       "lane rate confirmed by bench_tools/pipe_rates.cu (profiles/)",
+        "kernel": "reg pair kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
+        "evaluated_pairs_per_launch": pairs_per_launch, "mufu_per_pair": MUFU_PER_PAIR,
+        "algorithmic_bytes_per_launch": algo_bytes,
+        "hbm": {"achieved_gbs": algo_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
+                "note": "not the bound: ~5e3 pairs per algorithmic byte"},
+    }
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ------------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = cpu_reference_sample(case, 12.0, steps=1)
+            cpu_baseline = {"value": v, "unit": "Gpairs/s", "cores": info["cores"], "kind": info["kind"],
+                            "sample": info["sample"]}
+        except Exception as e:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": "Gpairs/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"failed: {e}"}
+
+    line = {
+        "metric": "reg_loss_fwd_bwd_throughput", "value": value, "unit": "Gpairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "B": B, "Z": Z, "R": R, "gamma": gamma, "delta": delta,
+                   "pairs_per_step": pairs, "parallelism": f"row-block x{world}" if world > 1 else "single GPU",
+                   "algo": args.algo,
+                   "l2_flush": "256 MiB memset before every step, inside the timed region (inputs are ~6 MB, far below L2)"},
+        "clocks": clocks, "e2e": {"value": e2e_value, "unit": "Gpairs/s", "ms_per_step": ms_e2e,
+                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "loss": loss_val, "loss_e2e": loss_e2e,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

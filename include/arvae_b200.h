@@ -1,0 +1,174 @@
+/*
+ * arvae_b200.h -- C ABI of libarvae_b200.so: AR-VAE's attribute-regularization
+ * hot path as hand-written CUDA for sm_100a (NVIDIA B200).
+ *
+ * The reference (ashispati/ar-vae) is pure Python/PyTorch and has no FFI of its
+ * own; the "interface" each entry point replaces is the reference function it
+ * computes.  All file:line citations are relative to the reference tree.
+ *
+ *   arvae_reg_loss_fwdbwd_f32      utils/trainer.py:369-403  Trainer.compute_reg_loss +
+ *                                   reg_loss_sign, the per-dim caller loop
+ *                                   imagevae/image_vae_trainer.py:171-180 /
+ *                                   measurevae/measure_vae_trainer.py:131-142, and the autograd
+ *                                   backward that utils/trainer.py:140 (loss.backward()) triggers
+ *   arvae_reg_loss_scatter_bwd_f32 the select-backward / accumulate step of that autograd graph
+ *   arvae_latent_head_fwd_f32      imagevae/mnist_vae.py:74-87 (reparametrize, rsample = loc+eps*scale),
+ *                                   measurevae/measure_vae.py:115-123, utils/trainer.py:354-367
+ *                                   (compute_kld_loss vs the unit prior)
+ *   arvae_latent_head_bwd_f32      autograd backward of the two above
+ *   arvae_reg_loss_host_f32        the same compute_reg_loss loop, host buffers in / out
+ *                                   (what a non-torch caller would bind)
+ *   arvae_reg_sign_matrix_i8       utils/trainer.py:394-395,400 (attribute sign matrix; debug/parity)
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types; `stream` is a cudaStream_t passed as void*.
+ *   - pointers named *_dev are device pointers on the current device; *_host are host pointers.
+ *   - every function returns 0 on success, a negative ARVAE_E_* code for argument errors and a
+ *     positive cudaError_t for CUDA failures; arvae_last_error() returns a thread-local message.
+ *   - all device work is stream-ordered; no function synchronises the device or allocates
+ *     device memory except arvae_reg_loss_host_f32 (which owns its buffers and synchronises
+ *     `stream` before returning).  Entry points are re-entrant.
+ *   - "rows" are samples i of the batch; "columns" are the samples j they are paired with.
+ *     A call covers the row block [row_begin,row_end) against ALL B_total columns, so one entry
+ *     serves single-GPU (0..B) and row-block sharding across GPUs.
+ */
+#ifndef ARVAE_B200_H
+#define ARVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARVAE_VERSION 100
+
+#if defined(__GNUC__)
+#define ARVAE_API __attribute__((visibility("default")))
+#else
+#define ARVAE_API
+#endif
+
+#define ARVAE_E_BADARG (-1)    /* null pointer, negative size, R out of range ... */
+#define ARVAE_E_WORKSPACE (-2) /* workspace too small */
+#define ARVAE_E_NODEVICE (-3)  /* no CUDA device / wrong architecture */
+
+#define ARVAE_MAX_REG_DIMS 32
+
+/* algorithm selector for arvae_reg_loss_fwdbwd_f32 */
+#define ARVAE_ALGO_AUTO 0
+#define ARVAE_ALGO_DENSE 1  /* every tile through the general pair loop (float compares)      */
+#define ARVAE_ALGO_SORTED 2 /* rows/columns ordered by attribute, constant-sign tile fast path */
+
+ARVAE_API int arvae_version(void);
+ARVAE_API const char *arvae_last_error(void);
+
+/* Number of SMs of the current device (cached); <0 on error. */
+ARVAE_API int arvae_device_sm_count(void);
+
+/* Bytes of scratch the fused forward+backward needs for this shape. */
+ARVAE_API size_t arvae_reg_loss_workspace_bytes(int64_t B_total, int64_t n_rows, int32_t R);
+
+/*
+ * Fused forward + backward of  sum_r gamma * mean_ij | tanh(factor*(z[i,d_r]-z[j,d_r])) - sign(a[i,c_r]-a[j,c_r]) |
+ * restricted to rows i in [row_begin,row_end), j over all B_total samples.
+ *
+ *   z_dev          [B_total, *] float, element strides (z_row_stride, z_col_stride)
+ *   labels_dev     [B_total, *] float, element strides (lab_row_stride, lab_col_stride)
+ *   reg_dims_host  [R] latent column d_r   (0 <= d_r)
+ *   label_cols_host[R] label column c_r    (the trainers use c_r == d_r)
+ *   loss_out_dev   [1] double: the block's share of the loss, ALREADY scaled by gamma / B_total^2
+ *                  (shares of disjoint row blocks add up to the reference's value)
+ *   loss_f32_out_dev [1] float or NULL: the same value rounded to float (the reference's dtype)
+ *   grad_cols_out_dev [n_rows, R] float or NULL: d loss / d z[row_begin+k, d_r]  (full-matrix
+ *                  gradient of the mean loss, times gamma), NULL skips the gradient math
+ *   row_loss_out_dev  [n_rows, R] double or NULL: per-row unnormalised sums  sum_j |t_ij - s_ij|
+ *                  (parity/debug output)
+ */
+ARVAE_API int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t z_col_stride,
+                              const float *labels_dev, int64_t lab_row_stride,
+                              int64_t lab_col_stride, const int32_t *reg_dims_host,
+                              const int32_t *label_cols_host, int32_t R, int64_t row_begin,
+                              int64_t row_end, int64_t B_total, float gamma, float factor,
+                              int32_t algo, double *loss_out_dev, float *loss_f32_out_dev,
+                              float *grad_cols_out_dev, double *row_loss_out_dev,
+                              void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/*
+ * grad_z[k, :] = 0 ; grad_z[k, d_r] += grad_out * grad_cols[k, r]   for k in [0,n_rows)
+ *   grad_out_dev [1] float (upstream gradient of the scalar loss) or NULL for 1.0
+ *   grad_z_dev   [n_rows, Z] float with row stride gz_row_stride; every element is written.
+ */
+ARVAE_API int arvae_reg_loss_scatter_bwd_f32(const float *grad_cols_dev, const float *grad_out_dev,
+                                   const int32_t *reg_dims_host, int32_t R, int64_t n_rows,
+                                   int64_t Z, float *grad_z_dev, int64_t gz_row_stride,
+                                   void *stream);
+
+/*
+ * Latent head forward (one pass over [B,Z]):
+ *   z       = loc + eps*scale                                   (bit-identical to Normal.rsample)
+ *   kld_sum = sum_b sum_d 0.5*(scale^2 + loc^2 - 1 - log(scale^2))
+ *   kld_mean = kld_sum / B ;  kld_loss = beta * |kld_mean - capacity| ;
+ *   kcoef    = beta * sgn(kld_mean - capacity) / B              (what the backward needs)
+ *   loc/scale/eps/z  [B,Z] float contiguous
+ *   kld_sum_out_dev  [1] double;  kld_mean/kld_loss/kcoef_out_dev  [1] float each, or NULL
+ *   ws_dev: scratch of arvae_latent_head_workspace_bytes(B,Z) bytes.
+ */
+ARVAE_API size_t arvae_latent_head_workspace_bytes(int64_t B, int64_t Z);
+ARVAE_API int arvae_latent_head_fwd_f32(const float *loc_dev, const float *scale_dev, const float *eps_dev,
+                              int64_t B, int64_t Z, float beta, float capacity, float *z_out_dev,
+                              double *kld_sum_out_dev, float *kld_mean_out_dev,
+                              float *kld_loss_out_dev, float *kcoef_out_dev, void *ws_dev,
+                              size_t ws_bytes, void *stream);
+
+/*
+ * Latent head backward (one pass over [B,Z]):
+ *   dloc   = dz + k * loc
+ *   dscale = dz * eps + k * (scale - 1/scale)
+ * with dz[b,d] = dz_up[b,d] + greg * grad_cols[b,r] (summed over r with d_r == d) and
+ *   k = kscale * (kcoef_dev ? *kcoef_dev : 1) * (gkld_dev ? *gkld_dev : 1).
+ *   dz_up_dev [B,Z] or NULL (-> 0); grad_cols_dev [B,R] or NULL; greg_dev [1] float or NULL (-> 1)
+ *   dloc_dev / dscale_dev [B,Z] float, either may be NULL.
+ */
+ARVAE_API int arvae_latent_head_bwd_f32(const float *loc_dev, const float *scale_dev, const float *eps_dev,
+                              const float *dz_up_dev, const float *grad_cols_dev,
+                              const float *greg_dev, const int32_t *reg_dims_host, int32_t R,
+                              float kscale, const float *kcoef_dev, const float *gkld_dev,
+                              int64_t B, int64_t Z, float *dloc_dev, float *dscale_dev,
+                              void *stream);
+
+/*
+ * Host-buffer form of the compute_reg_loss loop (the end-to-end call): copies z and labels to the
+ * device, runs the fused forward+backward over all rows, copies the loss and dLoss/dz back.
+ *   z_host [B,Z] float row-major, labels_host [B,A] float row-major
+ *   loss_out_host [1] float, grad_z_out_host [B,Z] float or NULL
+ * Device buffers are cached per thread between calls of the same shape; arvae_host_release() frees them.
+ */
+ARVAE_API int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z, const float *labels_host,
+                            int64_t A, const int32_t *reg_dims_host,
+                            const int32_t *label_cols_host, int32_t R, float gamma, float factor,
+                            int32_t algo, float *loss_out_host, float *grad_z_out_host,
+                            void *stream);
+ARVAE_API void arvae_host_release(void);
+
+/* s[i*B+j] = sign(a_i - a_j) as int8, for parity tests at small B (same compare the kernels use). */
+ARVAE_API int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
+                             int8_t *out_dev, void *stream);
+
+/*
+ * Optional timing of the dominant (pair) kernel alone, for roofline reporting: while enabled, each
+ * fused forward+backward brackets its pair-kernel launch with CUDA events on the caller's stream
+ * (a ring of the last 64 launches per thread). arvae_profile_pair_kernel_ms synchronises those
+ * events, returns the summed milliseconds and launch count since the last call, and clears the ring.
+ */
+ARVAE_API void arvae_profile_enable(int on);
+ARVAE_API int arvae_profile_pair_kernel_ms(float *sum_ms_out, int *n_out);
+
+/* Number of kernel launches issued through the library (all threads) since the last reset. */
+ARVAE_API int64_t arvae_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARVAE_B200_H */

@@ -1,0 +1,388 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+
+* the committed golden vectors (outputs of the unmodified reference, tests/golden/), and
+* the CPU oracle (oracle/, float64 mode) on the same seeded inputs, including batch sizes the
+  reference cannot allocate, where row samples and size-independent properties are used.
+
+Bars (tests/util.py): loss 1e-5 relative; gradient 1e-5 of the column max; sign matrix bit-exact.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_names
+from util import assert_grad_close, assert_loss_close
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = [1]  # ARVAE_ALGO_DENSE; the sorted path adds itself below when it exists
+try:
+    from arvae_b200 import ops as _ops
+    if getattr(_ops, "HAVE_SORTED", False):
+        ALGOS.append(2)
+except Exception:  # pragma: no cover
+    pass
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import arvae_b200
+    from arvae_b200 import _lib
+    assert torch.cuda.is_available(), "these tests need the B200"
+    _lib.load()  # fail loudly if the extension is missing
+    return arvae_b200
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors from the unmodified reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", golden_names("reg_c"))
+def test_fused_dim_loop_matches_reference(ab, name, algo):
+    g = golden(name)
+    z = dev(g["z"]).requires_grad_(True)
+    labels = dev(g["labels"])
+    dims = tuple(int(d) for d in g["reg_dims"])
+    loss = ab.reg_loss_fused(z, labels, dims, float(g["gamma"]), float(g["delta"]), algo=algo)
+    assert loss.dtype == torch.float32 and loss.dim() == 0
+    loss.backward()
+    assert_loss_close(loss.item(), g["loss"])
+    assert_grad_close(z.grad.cpu().numpy(), g["grad_z"])
+    untouched = [d for d in range(z.shape[1]) if d not in dims]
+    assert not z.grad[:, untouched].any()
+
+
+@pytest.mark.parametrize("name", ["reg_c1_mnist_b64", "reg_c2_dsprites_b512"])
+def test_per_dim_calls_like_the_trainers(ab, name):
+    """imagevae/image_vae_trainer.py:171-180: one call per dim with the strided view labels[:, dim]."""
+    g = golden(name)
+    z = dev(g["z"]).requires_grad_(True)
+    labels = dev(g["labels"])
+    gamma, delta = float(g["gamma"]), float(g["delta"])
+    reg_loss = 0.0
+    for k, dim in enumerate(int(d) for d in g["reg_dims"]):
+        view = labels[:, dim]
+        assert not view.is_contiguous() or labels.shape[1] == 1
+        one = ab.compute_reg_loss(z, view, dim, gamma=gamma, factor=delta)
+        assert_loss_close(one.item(), g["per_dim_loss"][k])
+        reg_loss += one
+    reg_loss.backward()
+    assert_loss_close(reg_loss.item(), g["loss"])
+    assert_grad_close(z.grad.cpu().numpy(), g["grad_z"])
+
+
+def test_single_call_negative_dim(ab):
+    g = golden("reg_single_negdim")
+    z = dev(g["z"]).requires_grad_(True)
+    labels = dev(g["labels"])
+    loss = ab.compute_reg_loss(z, labels[:, int(g["label_col"])], int(g["reg_dim"]), float(g["gamma"]),
+                               factor=float(g["delta"]))
+    loss.backward()
+    assert_loss_close(loss.item(), g["loss"])
+    assert_grad_close(z.grad.cpu().numpy(), g["grad_z"])
+
+
+def test_tuple_reg_dim_extension_and_tensor_scalars(ab):
+    g = golden("reg_c1_mnist_b64")
+    z = dev(g["z"])
+    labels = dev(g["labels"])
+    dims = tuple(int(d) for d in g["reg_dims"])
+    loss = ab.compute_reg_loss(z, labels, dims, torch.tensor(float(g["gamma"])), torch.tensor([float(g["delta"])]))
+    assert not loss.requires_grad
+    assert_loss_close(loss.item(), g["loss"])
+
+
+# ------------------------------------------------------------------------------------------------
+# sign matrix: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_sign_matrix_bit_exact_vs_reference(ab, oracle_mod):
+    g = golden("sign_matrix_special")
+    s = ab.sign_matrix(dev(g["a"])).cpu().numpy()
+    assert s.dtype == np.int8
+    assert np.array_equal(s, g["sign"])
+    assert np.array_equal(s, oracle_mod.sign_matrix(g["a"]))
+    x = dev(g["x"]).requires_grad_(True)
+    loss = ab.reg_loss_sign(x, dev(g["a"]), factor=float(g["delta"]))
+    loss.backward()
+    assert_loss_close(loss.item(), g["loss"])
+    assert_grad_close(x.grad.cpu().numpy(), g["grad_x"])
+
+
+def test_sign_matrix_bit_exact_on_dataset_like_labels(ab, oracle_mod):
+    from arvae_b200 import synth
+    for kind, col in (("dsprites", 1), ("dsprites", 3), ("music", 0), ("morpho", 4)):
+        lab = synth.make_labels(kind, 700, 7)[:, col].contiguous()
+        got = ab.sign_matrix(lab.cuda()).cpu().numpy()
+        assert np.array_equal(got, oracle_mod.sign_matrix(lab.numpy()))
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases the reference handles
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", golden_names("edge_"))
+def test_edge_cases(ab, name, algo):
+    g = golden(name)
+    x = dev(g["x"], torch.float32).requires_grad_(True)
+    a = dev(g["a"])  # int64 / float64 labels stay in their dtype: sign is taken there
+    if algo == 1:
+        loss = ab.reg_loss_sign(x, a, factor=float(g["delta"]))
+    else:
+        loss = ab.reg_loss_fused(x.reshape(-1, 1), a.reshape(-1, 1), (0,), 1.0, float(g["delta"]), algo=algo)
+    loss.backward()
+    assert_loss_close(loss.item(), g["loss"])
+    assert_grad_close(x.grad.cpu().numpy(), g["grad_x"])
+    if name in ("edge_all_equal_both", "edge_b1"):
+        assert loss.item() == 0.0 and not x.grad.any()
+
+
+def test_empty_batch_gives_nan_like_the_reference(ab):
+    z = torch.zeros(0, 4, device="cuda")
+    lab = torch.zeros(0, 4, device="cuda")
+    assert torch.isnan(ab.reg_loss_fused(z, lab, (1, 2), 1.0, 1.0))
+    assert torch.isnan(ab.compute_reg_loss(z, lab[:, 0], 0, 1.0))
+
+
+def test_length_mismatch_raises_runtime_error(ab):
+    z = torch.zeros(6, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="must match"):
+        ab.compute_reg_loss(z, torch.zeros(5, device="cuda"), 0, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# against the float64 oracle on seeded inputs (sizes the oracle finishes in seconds)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("B,delta,kind", [(1537, 1.0, "morpho"), (2048, 10.0, "music"), (3000, 1.0, "dsprites"),
+                                          (257, 0.05, "morpho"), (1024, 25.0, "dsprites")])
+def test_against_f64_oracle(ab, oracle_mod, B, delta, kind, algo):
+    from arvae_b200 import synth
+    g = torch.Generator().manual_seed(B)
+    labels = synth.make_labels(kind, B, B + 1)
+    Z = labels.shape[1]
+    z = torch.randn(B, Z, generator=g)
+    dims = tuple(range(1, Z)) if kind != "music" else tuple(range(Z))
+    ref_loss, ref_grad = oracle_mod.compute_reg_loss_multi(z.numpy(), labels.numpy(), dims, 2.0, delta, f64=True)
+    zc = z.cuda().requires_grad_(True)
+    loss = ab.reg_loss_fused(zc, labels.cuda(), dims, 2.0, delta, algo=algo)
+    loss.backward()
+    assert_loss_close(loss.item(), ref_loss)
+    assert_grad_close(zc.grad.cpu().numpy(), ref_grad)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_random_labels_worst_case_for_cancellation(ab, oracle_mod, algo):
+    """Labels independent of z: row gradient sums cancel to O(sqrt(B)), the hardest case for the
+    absolute accuracy of the fp32 partial sums."""
+    B = 4096
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(B, 3, generator=g)
+    labels = torch.randn(B, 3, generator=g)
+    ref_loss, ref_grad = oracle_mod.compute_reg_loss_multi(z.numpy(), labels.numpy(), (0, 1, 2), 1.0, 1.0, f64=True)
+    zc = z.cuda().requires_grad_(True)
+    loss = ab.reg_loss_fused(zc, labels.cuda(), (0, 1, 2), 1.0, 1.0, algo=algo)
+    loss.backward()
+    assert_loss_close(loss.item(), ref_loss)
+    assert_grad_close(zc.grad.cpu().numpy(), ref_grad)
+
+
+# ------------------------------------------------------------------------------------------------
+# row blocks (the multi-GPU sharding unit), determinism
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
+def test_row_blocks_add_up_and_rows_are_bitwise_identical(ab, algo):
+    g = golden("reg_c2_dsprites_b4096")
+    z = dev(g["z"])
+    labels = dev(g["labels"])
+    dims = tuple(int(d) for d in g["reg_dims"])
+    gamma, delta = float(g["gamma"]), float(g["delta"])
+    B = z.shape[0]
+    full_loss, full_grad, full_rows = ab.reg_loss_rows(z, labels, dims, gamma, delta, 0, B, algo=algo,
+                                                       want_row_loss=True)
+    edges = [0, 1, 513, 2048, 4095, 4096]
+    parts, grads, rows = [], [], []
+    for r0, r1 in zip(edges[:-1], edges[1:]):
+        l, gc, rl = ab.reg_loss_rows(z, labels, dims, gamma, delta, r0, r1, algo=algo, want_row_loss=True)
+        parts.append(l.item())
+        grads.append(gc)
+        rows.append(rl)
+    assert abs(sum(parts) - full_loss.item()) <= 1e-12 * abs(full_loss.item())
+    assert torch.equal(torch.cat(grads, 0), full_grad)  # each row sweeps the same columns in the same order
+    assert torch.equal(torch.cat(rows, 0), full_rows)
+    assert_loss_close(full_loss.item(), g["loss"])
+    # per-row sums add up to the loss
+    tot = full_rows.sum().item() * gamma / (B * B)
+    assert abs(tot - full_loss.item()) <= 1e-12 * abs(tot)
+
+
+def test_run_to_run_bitwise_reproducible(ab):
+    from arvae_b200 import synth
+    c = synth.make_case("c4_mnist_b65536", B=8192)
+    z, labels = c["z"].cuda(), c["labels"].cuda()
+    outs = []
+    for _ in range(3):
+        zz = z.clone().requires_grad_(True)
+        l = ab.reg_loss_fused(zz, labels, c["reg_dims"], c["gamma"], c["delta"])
+        l.backward()
+        outs.append((l.clone(), zz.grad.clone()))
+    for l, gr in outs[1:]:
+        assert torch.equal(l, outs[0][0]) and torch.equal(gr, outs[0][1])
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size config (C4: B=65536, R=6): row samples against the oracle + size-independent properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
+def test_c4_full_size_row_samples_and_properties(ab, oracle_mod, algo):
+    from arvae_b200 import synth
+    c = synth.make_case("c4_mnist_b65536")
+    z, labels = c["z"], c["labels"]
+    B = c["B"]
+    dims = c["reg_dims"]
+    zc, lc = z.cuda(), labels.cuda()
+    loss64, grad_cols, row_loss = ab.reg_loss_rows(zc, lc, dims, c["gamma"], c["delta"], 0, B, algo=algo,
+                                                   want_row_loss=True)
+    torch.cuda.synchronize()
+    grad_cols = grad_cols.cpu().numpy()
+    row_loss = row_loss.cpu().numpy()
+    # (1) sampled rows vs the float64 oracle: per-row loss sums and gradients
+    rows = np.r_[0, 1, 511, 512, 8191, 30000, 65534, 65535, np.random.RandomState(0).randint(0, B, 24)]
+    scale = np.abs(grad_cols).max(axis=0)
+    for r, dim in enumerate(dims):
+        x = z[:, dim].numpy().astype(np.float64)
+        a = labels[:, dim].numpy().astype(np.float64)
+        for i in rows:
+            _, rl, g = oracle_mod.reg_rows(x, a, c["delta"], int(i), int(i) + 1, f64=True)
+            assert abs(row_loss[i, r] - rl[0]) <= 1e-6 * rl[0], (i, r, row_loss[i, r], rl[0])
+            assert abs(grad_cols[i, r] - c["gamma"] * g[0]) <= 1e-5 * scale[r], (i, r)
+    # (2) the loss is the sum of the row sums, and lies in [0, 2*gamma*R]
+    tot = row_loss.sum() * c["gamma"] / (float(B) * float(B))
+    assert abs(tot - loss64.item()) <= 1e-12 * tot
+    assert 0.0 < loss64.item() < 2.0 * c["gamma"] * len(dims)
+    # (3) antisymmetry: gradients of a pairwise-difference loss sum to zero over the batch
+    colsum = grad_cols.astype(np.float64).sum(axis=0)
+    assert np.all(np.abs(colsum) <= 1e-5 * scale * np.sqrt(B)), colsum
+    # (4) invariance: shifting a latent column by a constant changes nothing but rounding
+    z2 = zc.clone()
+    z2[:, dims[0]] += 0.5
+    loss_shift, _, _ = ab.reg_loss_rows(z2, lc, dims, c["gamma"], c["delta"], 0, B, want_grad=False, algo=algo)
+    assert_loss_close(loss_shift.item(), loss64.item(), 2e-6)
+    # (5) a monotone transform of the labels leaves the sign matrix, hence everything, unchanged
+    l2 = lc.clone()
+    l2[:, dims[1]] = l2[:, dims[1]] * 3.0 + 1.0
+    loss_mono, g_mono, _ = ab.reg_loss_rows(zc, l2, dims, c["gamma"], c["delta"], 0, B, algo=algo)
+    assert torch.equal(loss_mono, loss64)
+    assert np.array_equal(g_mono.cpu().numpy(), grad_cols)
+
+
+# ------------------------------------------------------------------------------------------------
+# latent head: reparametrize + KLD (+ reg) fused
+# ------------------------------------------------------------------------------------------------
+def test_fused_head_matches_reference(ab):
+    g = golden("head_c3_measure_b2048")
+    loc = dev(g["loc"]).requires_grad_(True)
+    log_std = dev(g["log_std"]).requires_grad_(True)
+    scale = torch.exp(log_std)  # encoder side stays stock PyTorch (measurevae/encoder.py:120-123)
+    scale.retain_grad()
+    dims = tuple(int(d) for d in g["reg_dims"])
+    z, kld, reg = ab.reparam_kld_reg(loc, scale, dev(g["eps"]), dev(g["labels"]), dims, float(g["beta"]),
+                                     float(g["capacity"]), float(g["gamma"]), float(g["delta"]))
+    assert np.array_equal(z.detach().cpu().numpy(), g["z_tilde"])  # bit-identical rsample
+    assert_loss_close(kld.item(), g["kld_loss"])
+    assert_loss_close(reg.item(), g["reg_loss"])
+    (kld + reg).backward()
+    assert_grad_close(loc.grad.cpu().numpy(), g["grad_loc"])
+    assert_grad_close(scale.grad.cpu().numpy(), g["grad_scale"])
+    assert_grad_close(log_std.grad.cpu().numpy(), g["grad_log_std"])
+
+
+def test_fused_head_with_decoder_gradient(ab):
+    """z_tilde also feeds the decoder: its upstream gradient must flow through the same backward."""
+    g = golden("head_c3_measure_b2048")
+    w = torch.linspace(-1, 1, g["loc"].size).reshape(g["loc"].shape).cuda()
+    outs = []
+    for fused in (True, False):
+        loc = dev(g["loc"]).requires_grad_(True)
+        scale = torch.exp(dev(g["log_std"])).requires_grad_(True)
+        dims = tuple(int(d) for d in g["reg_dims"])
+        if fused:
+            z, kld, reg = ab.reparam_kld_reg(loc, scale, dev(g["eps"]), dev(g["labels"]), dims, 4.0, 50.0, 1.0, 10.0)
+        else:  # composable pieces: head node + reg node, glued by autograd
+            z, kld_mean = ab.latent_head(loc, scale, dev(g["eps"]))
+            kld = 4.0 * (kld_mean - 50.0).abs()
+            reg = ab.reg_loss_fused(z, dev(g["labels"]), dims, 1.0, 10.0)
+        total = kld + reg + (z * w).sum()
+        total.backward()
+        outs.append((total.item(), loc.grad.clone(), scale.grad.clone()))
+    assert_loss_close(outs[0][0], outs[1][0], 1e-6)
+    assert_grad_close(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy(), 1e-6)
+    assert_grad_close(outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy(), 1e-6)
+    # and against plain torch autograd for the non-reg part
+    loc = dev(g["loc"]).requires_grad_(True)
+    scale = torch.exp(dev(g["log_std"])).requires_grad_(True)
+    d = torch.distributions.Normal(loc, scale)
+    zt = loc + dev(g["eps"]) * scale
+    kl = torch.distributions.kl.kl_divergence(d, torch.distributions.Normal(torch.zeros_like(loc), torch.ones_like(scale)))
+    ref = 4.0 * (kl.sum(1).mean() - 50.0).abs() + (zt * w).sum()
+    ref.backward()
+    loc2 = dev(g["loc"]).requires_grad_(True)
+    scale2 = torch.exp(dev(g["log_std"])).requires_grad_(True)
+    z, kld_mean = ab.latent_head(loc2, scale2, dev(g["eps"]))
+    (4.0 * (kld_mean - 50.0).abs() + (z * w).sum()).backward()
+    assert_grad_close(loc2.grad.cpu().numpy(), loc.grad.cpu().numpy())
+    assert_grad_close(scale2.grad.cpu().numpy(), scale.grad.cpu().numpy())
+
+
+def test_kld_drop_in_with_capacity_tensor(ab):
+    g = golden("kld_c1_capacity_tensor")
+    loc = dev(g["loc"]).requires_grad_(True)
+    scale = dev(g["scale"]).requires_grad_(True)
+    z_dist = torch.distributions.Normal(loc=loc, scale=scale)
+    torch.manual_seed(0)
+    z_tilde, z_prior, prior = ab.reparametrize(z_dist)
+    cap = torch.FloatTensor([float(g["capacity"][0])]).cuda()  # image_vae_trainer.py:94 passes a [1] tensor
+    k = ab.compute_kld_loss(z_dist, prior, beta=float(g["beta"]), c=cap)
+    assert tuple(k.shape) == (1,)
+    assert_loss_close(k.item(), g["kld_loss"][0])
+    k.sum().backward()
+    assert_grad_close(loc.grad.cpu().numpy(), g["grad_loc"])
+    assert_grad_close(scale.grad.cpu().numpy(), g["grad_scale"])
+    # RNG order of the reference: eps first, then the unused prior sample
+    torch.manual_seed(0)
+    eps = torch.distributions.utils._standard_normal(loc.shape, dtype=loc.dtype, device=loc.device)
+    zp = torch.normal(torch.zeros_like(loc), torch.ones_like(loc))
+    assert torch.equal(z_tilde.detach(), (loc + eps * scale).detach())
+    assert torch.equal(z_prior, zp)
+
+
+# ------------------------------------------------------------------------------------------------
+# the host-buffer C-ABI entry (what a non-torch caller binds)
+# ------------------------------------------------------------------------------------------------
+def test_host_buffer_entry_point(ab):
+    from arvae_b200 import _lib
+    lib = _lib.load()
+    g = golden("reg_c2_dsprites_b4096")
+    z = np.ascontiguousarray(g["z"])
+    labels = np.ascontiguousarray(g["labels"])
+    dims = [int(d) for d in g["reg_dims"]]
+    B, Z = z.shape
+    loss = ctypes.c_float()
+    grad = np.empty_like(z)
+    rc = lib.arvae_reg_loss_host_f32(z.ctypes.data_as(ctypes.c_void_p), B, Z,
+                                     labels.ctypes.data_as(ctypes.c_void_p), labels.shape[1],
+                                     _lib.i32_array(dims), _lib.i32_array(dims), len(dims), float(g["gamma"]),
+                                     float(g["delta"]), 0, ctypes.byref(loss),
+                                     grad.ctypes.data_as(ctypes.c_void_p), None)
+    assert rc == 0, _lib.last_error()
+    assert_loss_close(loss.value, g["loss"])
+    assert_grad_close(grad, g["grad_z"])
+    lib.arvae_host_release()
