@@ -32,6 +32,7 @@ SIGNATURES = {
     "arvae_reg_loss_fwdbwd_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _c_i32p, _c_i32p, _i32,
                                                  _i64, _i64, _i64, _f, _f, _i32, _vp, _vp, _vp, _vp, _vp,
                                                  _sz, _vp]),
+    "arvae_reg_loss_path_flags": (ctypes.c_int, [_i64, _i64, _i32, _i32, _vp, _c_i32p, _vp]),
     "arvae_reg_loss_scatter_bwd_f32": (ctypes.c_int, [_vp, _vp, _c_i32p, _i32, _i64, _i64, _vp, _i64, _vp]),
     "arvae_latent_head_workspace_bytes": (_sz, [_i64, _i64]),
     "arvae_latent_head_fwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp,

@@ -156,7 +156,9 @@ int arvae_device_sm_count(void) {
 
 size_t arvae_reg_loss_workspace_bytes(int64_t B_total, int64_t n_rows, int32_t R) {
     if (B_total < 0 || n_rows < 0 || R < 0 || R > ARVAE_MAX_REG_DIMS) return 0;
-    return dense_layout(B_total, n_rows, R > 0 ? R : 1, sm_count()).bytes;
+    const size_t d = dense_layout(B_total, n_rows, R > 0 ? R : 1, sm_count()).bytes;
+    const size_t s = sorted_layout(B_total, n_rows, R > 0 ? R : 1, sm_count()).bytes;
+    return d > s ? d : s;
 }
 
 int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t z_col_stride,
@@ -190,9 +192,12 @@ int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t 
     P.loss_out = loss_out_dev; P.loss_f32_out = loss_f32_out_dev; P.grad_cols_out = grad_cols_out_dev; P.row_loss_out = row_loss_out_dev;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
+    const bool sorted = algo == ARVAE_ALGO_SORTED || (algo == ARVAE_ALGO_AUTO && B_total >= kSortedMinBatch);
     const DenseLayout L = dense_layout(B_total, row_end - row_begin, R > 0 ? R : 1, sm_count());
-    if (workspace_bytes < L.bytes) {
-        set_error("workspace too small: %zu < %zu", workspace_bytes, L.bytes);
+    const SortedLayout LS = sorted_layout(B_total, row_end - row_begin, R > 0 ? R : 1, sm_count());
+    const size_t need = sorted ? LS.bytes : L.bytes;
+    if (workspace_bytes < need) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, need);
         return ARVAE_E_WORKSPACE;
     }
     if (R == 0) {  // empty dim tuple: the callers' loop adds nothing
@@ -200,7 +205,27 @@ int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t 
         if (loss_f32_out_dev) ARVAE_CUDA_TRY(cudaMemsetAsync(loss_f32_out_dev, 0, sizeof(float), st));
         return 0;
     }
+    if (sorted) return run_reg_sorted(P, LS, reinterpret_cast<char *>(workspace_dev), st);
     return run_reg_dense(P, L, reinterpret_cast<char *>(workspace_dev), st);
+}
+
+int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_t algo,
+                              const void *workspace_dev, int32_t *flags_out_host, void *stream) {
+    if (B_total < 0 || n_rows < 0 || R <= 0 || R > ARVAE_MAX_REG_DIMS || !workspace_dev || !flags_out_host) {
+        set_error("bad argument to path_flags");
+        return ARVAE_E_BADARG;
+    }
+    const bool sorted = algo == ARVAE_ALGO_SORTED || (algo == ARVAE_ALGO_AUTO && B_total >= kSortedMinBatch);
+    if (!sorted) {
+        set_error("dense path selected for this shape: 2 MUFU per pair");
+        return ARVAE_E_BADARG;
+    }
+    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count());
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ARVAE_CUDA_TRY(cudaMemcpyAsync(flags_out_host, reinterpret_cast<const char *>(workspace_dev) + LS.off_flags,
+                                   sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st));
+    ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int arvae_reg_loss_scatter_bwd_f32(const float *grad_cols_dev, const float *grad_out_dev,

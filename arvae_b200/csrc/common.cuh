@@ -54,6 +54,12 @@ __device__ __forceinline__ float pair_sign(float ai, float aj) {
     return (ai > aj ? 1.0f : 0.0f) - (ai < aj ? 1.0f : 0.0f);
 }
 
+// xs = sgn(f) * x: the pair kernels work on xs so that sgn(tanh(f (x_i - x_j))) = sgn(xs_i - xs_j)
+// exactly (f == 0 gives xs = 0: tanh(0) = 0 for every pair, as in the reference).
+__device__ __forceinline__ float signed_latent(float x, float fsign) {
+    return fsign > 0.0f ? x : (fsign < 0.0f ? -x : 0.0f);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -65,7 +71,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Column padding: (u = +inf, a = NaN) makes a padded column contribute exactly |t - s| = 1 and
+// Column padding: (xs = +inf, a = NaN) makes a padded column contribute exactly |t - s| = 1 and
 // gradient 0 to every row (2^-inf = 0 -> r = 1 -> t = -1; NaN compares false -> s = 0), so the
 // pair loops need no bounds checks and the host subtracts n_pad per row.
 #define ARVAE_PAD_U (__int_as_float(0x7f800000))

@@ -16,18 +16,18 @@
 namespace arvae {
 
 // ------------------------------------------------------------------------------------------------
-// pack: strided z / labels  ->  dense per-dim column vectors U[r][Bpad], A[r][Bpad]
+// pack: strided z / labels  ->  dense per-dim column vectors X[r][Bpad] = sgn(f) z, A[r][Bpad]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_columns_kernel(const float *__restrict__ z, int64_t zrs, int64_t zcs,
                     const float *__restrict__ lab, int64_t lrs, int64_t lcs, RegDims dims, int R,
-                    int64_t B, int64_t Bpad, float c, float *__restrict__ U,
+                    int64_t B, int64_t Bpad, float fsign, float *__restrict__ U,
                     float *__restrict__ A) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Bpad) return;
     if (j < B) {
         for (int r = 0; r < R; ++r) {
-            U[(int64_t)r * Bpad + j] = c * __ldg(z + j * zrs + (int64_t)dims.zcol[r] * zcs);
+            U[(int64_t)r * Bpad + j] = signed_latent(__ldg(z + j * zrs + (int64_t)dims.zcol[r] * zcs), fsign);
             A[(int64_t)r * Bpad + j] = __ldg(lab + j * lrs + (int64_t)dims.lcol[r] * lcs);
         }
     } else {
@@ -41,15 +41,20 @@ pack_columns_kernel(const float *__restrict__ z, int64_t zrs, int64_t zcs,
 // ------------------------------------------------------------------------------------------------
 // the pair loop
 // ------------------------------------------------------------------------------------------------
-// One pair.  r = 1/(1+2^d) = (1 - t)/2 with d = u_i - u_j  =>  t = 1 - 2r,  1 - t^2 = 4 (r - r^2).
-// v = t - s = (1 - s) - 2r ;  loss += |v| ;  grad += sgn(v) * (r - r^2)   (x4 applied at the end).
-// sgn(v) with sgn(0) = 0 is clamp(v * 2^40, -1, 1): every non-zero |v| that carries a non-negligible
-// (r - r^2) is >= 2^-24 (see DESIGN.md "sign of v"), and v == 0 gives exactly 0 as abs-backward does.
+// One pair.  With xs = sgn(f) x:  d = xs_i - xs_j (exact sign of t), r = 1/(1+2^(|c| d)) = (1 - t)/2
+//   =>  t = 1 - 2r,  1 - t^2 = 4 (r - r^2),  v = t - s = (1 - s) - 2r
+//   loss += |v| ;  grad += sgn(v) * (r - r^2)          (x4 applied at the end)
+// sgn(v) with sgn(0) = 0, as abs-backward has it: for s != 0 it is -s (or the factor (r - r^2) is
+// 0); for a tie it is sgn(t) = sgn(d), which MUST come from d itself -- near d = 0 the MUFU
+// approximations cannot be trusted for the sign of 1 - 2r, and (1 - t^2) is at its maximum there.
+//   q = -s * 2^127 + d * 2^60 ;  sgn = clamp(q, -1, 1)
+// is exact whenever |d| >= 2^-60 or d == 0 (d * 2^60 only outweighs 2^127 when tanh is saturated
+// and the factor is 0 anyway).
 template <bool GRAD>
-__device__ __forceinline__ void pair_general(float ui, float ai, float uj, float aj, float &lacc,
-                                             float &gacc) {
-    const float d = ui - uj;
-    const float e = ex2_approx(d);
+__device__ __forceinline__ void pair_general(float xi, float ai, float xj, float aj, float cabs,
+                                             float &lacc, float &gacc) {
+    const float d = xi - xj;
+    const float e = ex2_approx(d * cabs);
     const float r = rcp_approx(e + 1.0f);
     const float gt = ai > aj ? 1.0f : 0.0f;
     const float lt = ai < aj ? 1.0f : 0.0f;
@@ -58,14 +63,15 @@ __device__ __forceinline__ void pair_general(float ui, float ai, float uj, float
     lacc += fabsf(v);
     if (GRAD) {
         const float w4 = fmaf(-r, r, r);
-        const float sg = fminf(fmaxf(v * 1099511627776.0f, -1.0f), 1.0f);
+        const float q = fmaf(k - 1.0f, 1.7014118e38f, d * 1.1529215e18f);
+        const float sg = fminf(fmaxf(q, -1.0f), 1.0f);
         gacc = fmaf(sg, w4, gacc);
     }
 }
 
 template <int RI, bool GRAD>
 __global__ void __launch_bounds__(kDenseThreads)
-reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, int64_t Bpad,
+reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, float cabs, int64_t Bpad,
                  int64_t row_begin, int64_t row_end, int64_t rows_pad, int64_t chunk_cols,
                  double *__restrict__ pgrad, double *__restrict__ prow,
                  double *__restrict__ lossp) {
@@ -113,10 +119,10 @@ reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, int64
                 const float4 aj = *reinterpret_cast<const float4 *>(sa + s0 + q);
 #pragma unroll
                 for (int k = 0; k < RI; ++k) {
-                    pair_general<GRAD>(ui[k], ai[k], uj.x, aj.x, lacc[k], gacc[k]);
-                    pair_general<GRAD>(ui[k], ai[k], uj.y, aj.y, lacc[k], gacc[k]);
-                    pair_general<GRAD>(ui[k], ai[k], uj.z, aj.z, lacc[k], gacc[k]);
-                    pair_general<GRAD>(ui[k], ai[k], uj.w, aj.w, lacc[k], gacc[k]);
+                    pair_general<GRAD>(ui[k], ai[k], uj.x, aj.x, cabs, lacc[k], gacc[k]);
+                    pair_general<GRAD>(ui[k], ai[k], uj.y, aj.y, cabs, lacc[k], gacc[k]);
+                    pair_general<GRAD>(ui[k], ai[k], uj.z, aj.z, cabs, lacc[k], gacc[k]);
+                    pair_general<GRAD>(ui[k], ai[k], uj.w, aj.w, cabs, lacc[k], gacc[k]);
                 }
             }
 #pragma unroll
@@ -256,15 +262,15 @@ DenseLayout dense_layout(int64_t B_total, int64_t n_rows, int R, int sm_count) {
 
 template <int RI>
 static void launch_dense(const DenseLayout &L, int R, bool want_grad, const float *U,
-                         const float *A, int64_t row_begin, int64_t row_end, double *pgrad,
+                         const float *A, float cabs, int64_t row_begin, int64_t row_end, double *pgrad,
                          double *prow, double *lossp, cudaStream_t st) {
     dim3 grid((unsigned)L.n_row_blocks, (unsigned)L.n_chunks, (unsigned)R);
     if (want_grad)
         reg_dense_kernel<RI, true><<<grid, kDenseThreads, 0, st>>>(
-            U, A, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp);
+            U, A, cabs, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp);
     else
         reg_dense_kernel<RI, false><<<grid, kDenseThreads, 0, st>>>(
-            U, A, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp);
+            U, A, cabs, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp);
 }
 
 int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStream_t st) {
@@ -277,16 +283,18 @@ int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStrea
     const bool want_grad = P.grad_cols_out != nullptr;
 
     const double c = 2.0 * (double)P.factor * 1.4426950408889634074;  // 2 f log2(e)
+    const float fsign = P.factor > 0.f ? 1.0f : (P.factor < 0.f ? -1.0f : 0.0f);
+    const float cabs = P.factor != 0.f ? (float)fabs(c) : 1.0f;  // f == 0: xs == 0, any scale works
     pack_columns_kernel<<<(unsigned)ceil_div(L.Bpad, 256), 256, 0, st>>>(
-        P.z, P.zrs, P.zcs, P.lab, P.lrs, P.lcs, P.dims, P.R, P.B, L.Bpad, (float)c, U, A);
+        P.z, P.zrs, P.zcs, P.lab, P.lrs, P.lcs, P.dims, P.R, P.B, L.Bpad, fsign, U, A);
     ARVAE_LAUNCH_CHECK("pack_columns_kernel");
 
     if (L.n_units > 0) {
         profile_begin(st);
         if (L.RI == 4)
-            launch_dense<4>(L, P.R, want_grad, U, A, P.row_begin, P.row_end, pgrad, prow, lossp, st);
+            launch_dense<4>(L, P.R, want_grad, U, A, cabs, P.row_begin, P.row_end, pgrad, prow, lossp, st);
         else
-            launch_dense<1>(L, P.R, want_grad, U, A, P.row_begin, P.row_end, pgrad, prow, lossp, st);
+            launch_dense<1>(L, P.R, want_grad, U, A, cabs, P.row_begin, P.row_end, pgrad, prow, lossp, st);
         profile_end(st);
         ARVAE_LAUNCH_CHECK("reg_dense_kernel");
     }

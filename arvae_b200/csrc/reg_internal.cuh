@@ -48,6 +48,23 @@ int run_scatter_bwd(const float *grad_cols, const float *grad_out, const RegDims
                     int64_t n_rows, int64_t Z, float *grad_z, int64_t gzrs, cudaStream_t st);
 int run_sign_matrix(const float *a, int64_t stride, int64_t B, int8_t *out, cudaStream_t st);
 
+// attribute-sorted path (sort.cu, reg_sorted.cu)
+struct SortedLayout {
+    int64_t N;      // power-of-two size of the key arrays (sort padding)
+    int64_t Bpad;   // columns padded to a multiple of kSubCols
+    int n_row_tiles, S;
+    int64_t n_rr, F;
+    int G_max, max_segs;
+    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_pgrad, off_prow,
+        off_lossp, bytes;
+};
+int64_t sort_padded_size(int64_t B);
+int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, int64_t B,
+                  int64_t N, unsigned long long *keys, cudaStream_t st);
+SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count);
+int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStream_t st);
+constexpr int64_t kSortedMinBatch = 8192;  // ARVAE_ALGO_AUTO switches to the sorted path from here
+
 // latent head (latent_head.cu)
 size_t latent_head_ws_bytes(int64_t B, int64_t Z);
 int run_latent_head_fwd(const float *loc, const float *scale, const float *eps, int64_t B,

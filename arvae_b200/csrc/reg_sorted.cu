@@ -1,0 +1,524 @@
+// reg_sorted.cu -- attribute-sorted pair kernel (sm_100a): the fast path for large batches.
+//
+// Same arithmetic as reg_dense.cu (reference utils/trainer.py:390-401 and its autograd backward),
+// reorganised so that almost every pair costs 1 MUFU + 4 FP32 instructions instead of 2 + 12:
+//
+//  * rows and columns of each regularised dim are ordered by attribute value (sort.cu).  A tile of
+//    512 rows x 256 columns whose attribute ranges do not overlap has a CONSTANT sign s_ij, so per
+//    pair only sum(r) and sum(r^2) are needed, r = (1 - t)/2:
+//        s = +1:  |t - s| = 2r        g = -(1 - t^2) = -4 (r - r^2)
+//        s = -1:  |t - s| = 2(1 - r)  g = +4 (r - r^2)
+//    Tiles inside one tie group (all attributes equal, incl. NaN rows/columns: NaN ties with
+//    everything) have s = 0:  |t| = 2 |1/2 - r|, g = sgn(1/2 - r) 4 (r - r^2).  Only tiles that
+//    straddle the diagonal band / a tie-group edge run the general loop with per-pair float
+//    compares of the raw attributes -- the sign is exact by construction in all three classes.
+//  * r = 1/(1 + 2^(u_i-u_j)) = E_j / (E_i + E_j) with u = 2 f log2(e) x and E = 2^u precomputed once
+//    per element: one MUFU.RCP per pair.  Safe while |u| <= 62 for every element of the dim (no
+//    overflow in E_i+E_j, full relative accuracy in both saturation directions); a per-dim flag
+//    computed by the gather kernel falls back to the 2-MUFU form (EX2 + RCP on the scaled latent
+//    difference) otherwise.
+//  * wherever a pair can be a tie (tie and general tiles), sgn(t) is taken from the exact float
+//    difference xs_i - xs_j of the (sign-adjusted) latents, never from the approximated tanh: near
+//    t = 0 the factor (1 - t^2) is maximal and abs-backward's sgn(0) = 0 must hold exactly for
+//    equal latents (the diagonal, duplicated samples).
+//  * work is split into fine units (row tile, 256-column sub-chunk) laid out linearly and divided
+//    EVENLY over a persistent grid (one contiguous range per CTA), so there is no wave tail; row
+//    partials go to a deterministic (segment, row tile) slot and are reduced in fixed order.
+#include "common.cuh"
+#include "reg_internal.cuh"
+
+namespace arvae {
+
+constexpr int kTileThreads = 128;
+constexpr int kTileRI = 4;
+constexpr int kTileRows = kTileThreads * kTileRI;  // 512 rows per row tile
+constexpr int kStageCols = 2048;                   // columns staged per __syncthreads pair
+constexpr float kMufu1MaxAbsU = 62.0f;
+
+// ------------------------------------------------------------------------------------------------
+// gather the sorted order: Us/As/Es[r][k] for sorted position k, perm[r][k] = original index
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
+                     const float *__restrict__ z, int64_t zrs, int64_t zcs,
+                     const float *__restrict__ lab, int64_t lrs, int64_t lcs, RegDims dims,
+                     int64_t B, int64_t Bpad, float fsign, float cabs, float *__restrict__ Xs,
+                     float *__restrict__ As, float *__restrict__ Es, int *__restrict__ perm,
+                     int *__restrict__ flags) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (k >= Bpad) return;
+    const int64_t o = (int64_t)r * Bpad + k;
+    if (k < B) {
+        const int64_t idx = (int64_t)(unsigned int)(keys[(int64_t)r * N + k] & 0xFFFFFFFFull);
+        const float xs = signed_latent(__ldg(z + idx * zrs + (int64_t)dims.zcol[r] * zcs), fsign);
+        const float u = cabs * xs;
+        Xs[o] = xs;
+        As[o] = __ldg(lab + idx * lrs + (int64_t)dims.lcol[r] * lcs);
+        Es[o] = exp2f(u);
+        perm[o] = (int)idx;
+        if (!(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + r, 1);  // also catches NaN / inf
+    } else {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
+        Xs[o] = ARVAE_PAD_U;
+        As[o] = ARVAE_PAD_A;
+        Es[o] = 8.5070592e37f;  // 2^126: E_i + E_j stays finite, r = E_j / (E_i + E_j) = 1 exactly
+        perm[o] = -1;
+    }
+}
+
+// rowpos[r][m] = m-th sorted position whose original index lies in [row_begin,row_end)
+// (row-block sharding: this rank's rows, in attribute order).  One CTA per dim.
+__global__ void __launch_bounds__(1024)
+row_select_kernel(const int *__restrict__ perm, int64_t B, int64_t Bpad, int64_t row_begin,
+                  int64_t row_end, int64_t n_rows, int *__restrict__ rowpos) {
+    __shared__ int scount[1024];
+    const int r = blockIdx.x;
+    const int *p = perm + (int64_t)r * Bpad;
+    const int64_t per = ceil((double)B / 1024.0);
+    const int64_t k0 = min((int64_t)threadIdx.x * per, B), k1 = min(k0 + per, B);
+    int cnt = 0;
+    for (int64_t k = k0; k < k1; ++k) cnt += (p[k] >= row_begin && p[k] < row_end);
+    scount[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan
+        const int v = threadIdx.x >= o ? scount[threadIdx.x - o] : 0;
+        __syncthreads();
+        scount[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int64_t m = scount[threadIdx.x] - cnt;
+    int *out = rowpos + (int64_t)r * n_rows;
+    for (int64_t k = k0; k < k1; ++k)
+        if (p[k] >= row_begin && p[k] < row_end) out[m++] = (int)k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair loops over one 256-column sub-chunk staged in shared memory
+// ------------------------------------------------------------------------------------------------
+// Per-thread row operands of one row tile.
+struct RowRegs {
+    float e[kTileRI];  // 2^u_i          (1-MUFU form)
+    float x[kTileRI];  // sgn(f) x_i     (2-MUFU form, exact tie signs)
+    float a[kTileRI];  // attribute
+};
+
+template <bool MUFU1>
+__device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs) {
+    if (MUFU1) return rcp_approx(ei + ej) * ej;          // E_j / (E_i + E_j)
+    return rcp_approx(ex2_approx(d * cabs) + 1.0f);       // 1 / (1 + 2^(|c| (xs_i - xs_j)))
+}
+
+template <bool MUFU1, bool GRAD>
+__device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,
+                                           const float *__restrict__ sx, float cabs, bool positive,
+                                           double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+    float A1[kTileRI][4], A2[kTileRI][4];
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) A1[k][q] = A2[k][q] = 0.0f;
+    const float *sv = MUFU1 ? se : sx;
+#pragma unroll 2
+    for (int q = 0; q < kSubCols; q += 4) {
+        const float4 vj = *reinterpret_cast<const float4 *>(sv + q);
+        const float vv[4] = {vj.x, vj.y, vj.z, vj.w};
+#pragma unroll
+        for (int k = 0; k < kTileRI; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float r = MUFU1 ? pair_r<true>(R.e[k], vv[e], 0.0f, cabs)
+                                      : pair_r<false>(0.0f, 0.0f, R.x[k] - vv[e], cabs);
+                A1[k][e] += r;
+                if (GRAD) A2[k][e] = fmaf(r, r, A2[k][e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k) {
+        const float S1 = (A1[k][0] + A1[k][1]) + (A1[k][2] + A1[k][3]);
+        const float S2 = (A2[k][0] + A2[k][1]) + (A2[k][2] + A2[k][3]);
+        // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2)
+        dl[k] += (double)(positive ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
+        if (GRAD) dg[k] += (double)(positive ? S2 - S1 : S1 - S2);
+    }
+}
+
+template <bool MUFU1, bool GRAD>
+__device__ __forceinline__ void loop_tie(const RowRegs &R, const float *__restrict__ se,
+                                         const float *__restrict__ sx, float cabs,
+                                         double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+    float lacc[kTileRI], gacc[kTileRI];
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = 0.0f;
+#pragma unroll 2
+    for (int q = 0; q < kSubCols; q += 4) {
+        const float4 xj = *reinterpret_cast<const float4 *>(sx + q);
+        const float xx[4] = {xj.x, xj.y, xj.z, xj.w};
+        float ee[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MUFU1) {
+            const float4 ej = *reinterpret_cast<const float4 *>(se + q);
+            ee[0] = ej.x; ee[1] = ej.y; ee[2] = ej.z; ee[3] = ej.w;
+        }
+#pragma unroll
+        for (int k = 0; k < kTileRI; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = R.x[k] - xx[e];
+                const float r = pair_r<MUFU1>(R.e[k], ee[e], d, cabs);
+                const float h = 0.5f - r;  // t / 2
+                lacc[k] += fabsf(h);
+                if (GRAD) {
+                    const float w4 = fmaf(-r, r, r);
+                    const float sg = fminf(fmaxf(d * 8.5070592e37f, -1.0f), 1.0f);  // sgn(t) = sgn(d), exact
+                    gacc[k] = fmaf(sg, w4, gacc[k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k) {
+        dl[k] += (double)(2.0f * lacc[k]);
+        if (GRAD) dg[k] += (double)gacc[k];
+    }
+}
+
+template <bool MUFU1, bool GRAD>
+__device__ __forceinline__ void loop_general(const RowRegs &R, const float *__restrict__ se,
+                                             const float *__restrict__ sx,
+                                             const float *__restrict__ sa, float cabs,
+                                             double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+    float lacc[kTileRI], gacc[kTileRI];
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = 0.0f;
+#pragma unroll 2
+    for (int q = 0; q < kSubCols; q += 4) {
+        const float4 xj = *reinterpret_cast<const float4 *>(sx + q);
+        const float4 aj = *reinterpret_cast<const float4 *>(sa + q);
+        const float xx[4] = {xj.x, xj.y, xj.z, xj.w};
+        const float aa[4] = {aj.x, aj.y, aj.z, aj.w};
+        float ee[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MUFU1) {
+            const float4 ej = *reinterpret_cast<const float4 *>(se + q);
+            ee[0] = ej.x; ee[1] = ej.y; ee[2] = ej.z; ee[3] = ej.w;
+        }
+#pragma unroll
+        for (int k = 0; k < kTileRI; ++k) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = R.x[k] - xx[e];
+                const float r = pair_r<MUFU1>(R.e[k], ee[e], d, cabs);
+                const float gt = R.a[k] > aa[e] ? 1.0f : 0.0f;
+                const float lt = R.a[k] < aa[e] ? 1.0f : 0.0f;
+                const float kk = (1.0f - gt) + lt;  // 1 - s
+                const float v = fmaf(-2.0f, r, kk);
+                lacc[k] += fabsf(v);
+                if (GRAD) {
+                    const float w4 = fmaf(-r, r, r);
+                    // sgn(v): -s when s != 0, else sgn(d) (see reg_dense.cu: pair_general)
+                    const float q2 = fmaf(kk - 1.0f, 1.7014118e38f, d * 1.1529215e18f);
+                    const float sg = fminf(fmaxf(q2, -1.0f), 1.0f);
+                    gacc[k] = fmaf(sg, w4, gacc[k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k) {
+        dl[k] += (double)lacc[k];
+        if (GRAD) dg[k] += (double)gacc[k];
+    }
+}
+
+enum TileClass { kClassGeneral = 0, kClassPos = 1, kClassNeg = 2, kClassTie = 3 };
+
+// Class of (row tile with attribute range [amin,amax], column sub-chunk [cmin,cmax]); both sorted
+// ascending with NaN (and padding) last, so the end points are the true min / max.
+__device__ __forceinline__ int classify(float amin, float amax, float cmin, float cmax) {
+    const bool row_all_nan = amin != amin, row_has_nan = amax != amax;
+    const bool col_all_nan = cmin != cmin, col_has_nan = cmax != cmax;
+    if (row_all_nan || col_all_nan) return kClassTie;     // NaN compares false both ways: s = 0
+    if (row_has_nan || col_has_nan) return kClassGeneral;
+    if (cmax < amin) return kClassPos;                     // a_i >= amin > cmax >= a_j
+    if (cmin > amax) return kClassNeg;
+    if (amin == amax && cmin == cmax && amin == cmin) return kClassTie;
+    return kClassGeneral;
+}
+
+struct TilesArgs {
+    const float *Xs, *Es, *As;  // [R][Bpad] in sorted order: sgn(f) x, 2^u, attribute
+    float cabs;                 // |2 f log2(e)|
+    const int *rowpos;          // [R][n_rows] sorted positions of this call's rows, or null = identity
+    const int *flags;           // [R] non-zero: some |u| > 62, use the 2-MUFU form for this dim
+    int64_t Bpad, n_rows;
+    int n_row_tiles, S;         // S = Bpad / kSubCols sub-chunks per row tile
+    int64_t F;                  // fine units = R * n_row_tiles * S
+    int G;                      // persistent CTAs
+    int64_t n_rr;               // R * n_row_tiles
+    int force_general;          // treat every tile as general (unsorted input / debugging)
+    double *pgrad, *prow, *lossp;
+};
+
+__host__ __device__ __forceinline__ int64_t cta_of_unit(int64_t f, int64_t F, int64_t G) {
+    return ((f + 1) * G + F - 1) / F - 1;  // largest c with floor(c F / G) <= f
+}
+
+template <bool MUFU1, bool GRAD>
+__device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const float *se,
+                                               const float *sx, const float *sa, float cabs,
+                                               double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+    if (cls == kClassPos) loop_const<MUFU1, GRAD>(R, se, sx, cabs, true, dl, dg);
+    else if (cls == kClassNeg) loop_const<MUFU1, GRAD>(R, se, sx, cabs, false, dl, dg);
+    else if (cls == kClassTie) loop_tie<MUFU1, GRAD>(R, se, sx, cabs, dl, dg);
+    else loop_general<MUFU1, GRAD>(R, se, sx, sa, cabs, dl, dg);
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(kTileThreads)
+reg_tiles_kernel(TilesArgs a) {
+    __shared__ __align__(16) float se[kStageCols];
+    __shared__ __align__(16) float sx[kStageCols];
+    __shared__ __align__(16) float sa[kStageCols];
+    __shared__ double sred[kTileThreads / 32];
+
+    const int64_t c = blockIdx.x;
+    int64_t f = (c * a.F) / a.G;
+    const int64_t f_end = ((c + 1) * a.F) / a.G;
+    double lthread = 0.0;
+
+    while (f < f_end) {
+        const int64_t rr = f / a.S;
+        const int s0 = (int)(f % a.S);
+        const int s1 = (int)min((int64_t)a.S, (int64_t)s0 + (f_end - f));
+        const int r = (int)(rr / a.n_row_tiles);
+        const int I = (int)(rr % a.n_row_tiles);
+        const bool mufu1 = a.flags[r] == 0;
+        const float *Er = a.Es + (int64_t)r * a.Bpad;
+        const float *Xr = a.Xs + (int64_t)r * a.Bpad;
+        const float *Ar = a.As + (int64_t)r * a.Bpad;
+        const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
+
+        const int64_t m0 = (int64_t)I * kTileRows;
+        const int64_t mlast = min(m0 + kTileRows, a.n_rows) - 1;
+        const float amin = Ar[rp ? rp[m0] : m0];
+        const float amax = Ar[rp ? rp[mlast] : mlast];
+
+        RowRegs R;
+        bool valid[kTileRI];
+        double dl[kTileRI], dg[kTileRI];
+#pragma unroll
+        for (int k = 0; k < kTileRI; ++k) {
+            const int64_t m = m0 + threadIdx.x + (int64_t)k * kTileThreads;
+            valid[k] = m < a.n_rows;
+            const int64_t pos = valid[k] ? (rp ? (int64_t)rp[m] : m) : 0;
+            R.e[k] = valid[k] ? Er[pos] : 1.0f;
+            R.x[k] = valid[k] ? Xr[pos] : 0.0f;
+            R.a[k] = valid[k] ? Ar[pos] : amax;
+            dl[k] = 0.0;
+            dg[k] = 0.0;
+        }
+
+        const int64_t col_end = (int64_t)s1 * kSubCols;
+        for (int64_t cs = (int64_t)s0 * kSubCols; cs < col_end; cs += kStageCols) {
+            const int n = (int)min((int64_t)kStageCols, col_end - cs);
+            __syncthreads();
+            for (int q = threadIdx.x * 4; q < n; q += kTileThreads * 4) {
+                *reinterpret_cast<float4 *>(se + q) = *reinterpret_cast<const float4 *>(Er + cs + q);
+                *reinterpret_cast<float4 *>(sx + q) = *reinterpret_cast<const float4 *>(Xr + cs + q);
+                *reinterpret_cast<float4 *>(sa + q) = *reinterpret_cast<const float4 *>(Ar + cs + q);
+            }
+            __syncthreads();
+            for (int sub = 0; sub < n; sub += kSubCols) {
+                const int cls = a.force_general ? (int)kClassGeneral
+                                                : classify(amin, amax, sa[sub], sa[sub + kSubCols - 1]);
+                if (mufu1) sweep_subchunk<true, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
+                else sweep_subchunk<false, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
+            }
+        }
+
+        // this CTA's segment of row tile rr: deterministic slot (segment index, rr)
+        const int64_t seg = c - cta_of_unit(rr * a.S, a.F, a.G);
+        const int64_t slot = (seg * a.n_rr + rr) * kTileRows;
+#pragma unroll
+        for (int k = 0; k < kTileRI; ++k) {
+            const int64_t o = slot + threadIdx.x + (int64_t)k * kTileThreads;
+            if (valid[k]) lthread += dl[k];
+            if (GRAD) a.pgrad[o] = dg[k];
+            if (a.prow) a.prow[o] = dl[k];
+        }
+        f += (s1 - s0);
+    }
+
+    lthread = warp_sum(lthread);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = lthread;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kTileThreads / 32; ++w) t += sred[w];
+        a.lossp[c] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int64_t row_begin,
+                          double gscale, double lscale, double pad_per_row,
+                          float *__restrict__ grad_cols, double *__restrict__ row_loss,
+                          double *__restrict__ loss_out, float *__restrict__ loss_f32_out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over R * n_rows, m fastest
+    if (idx < (int64_t)R * a.n_rows) {
+        const int r = (int)(idx / a.n_rows);
+        const int64_t m = idx % a.n_rows;
+        const int64_t I = m / kTileRows, lr = m % kTileRows;
+        const int64_t rr = (int64_t)r * a.n_row_tiles + I;
+        const int64_t c0 = cta_of_unit(rr * a.S, a.F, a.G);
+        const int64_t c1 = cta_of_unit(rr * a.S + a.S - 1, a.F, a.G);
+        const int64_t pos = a.rowpos ? (int64_t)a.rowpos[(int64_t)r * a.n_rows + m] : m;
+        const int64_t out = ((int64_t)perm[(int64_t)r * a.Bpad + pos] - row_begin) * R + r;
+        if (grad_cols) {
+            double g = 0.0;
+            for (int64_t seg = 0; seg <= c1 - c0; ++seg) g += a.pgrad[(seg * a.n_rr + rr) * kTileRows + lr];
+            grad_cols[out] = (float)(g * gscale);
+        }
+        if (row_loss) {
+            double l = 0.0;
+            for (int64_t seg = 0; seg <= c1 - c0; ++seg) l += a.prow[(seg * a.n_rr + rr) * kTileRows + lr];
+            row_loss[out] = l - pad_per_row;
+        }
+    }
+    if (blockIdx.x == 0) {
+        __shared__ double sh[256];
+        double t = 0.0;
+        for (int64_t u = threadIdx.x; u < a.G; u += 256) t += a.lossp[u];
+        sh[threadIdx.x] = t;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double total = sh[0] - pad_per_row * (double)a.n_rows * (double)R;
+            *loss_out = total * lscale;
+            if (loss_f32_out) *loss_f32_out = (float)(total * lscale);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int tiles_ctas_per_sm(bool grad) {
+    static int cache[2] = {0, 0};
+    int &v = cache[grad ? 1 : 0];
+    if (v == 0) {
+        int n = 0;
+        cudaError_t e = grad ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<true>, kTileThreads, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<false>, kTileThreads, 0);
+        if (e != cudaSuccess || n <= 0) {
+            (void)cudaGetLastError();
+            n = 4;
+        }
+        v = n;
+    }
+    return v;
+}
+
+SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count) {
+    SortedLayout L;
+    L.N = sort_padded_size(B_total > 0 ? B_total : 1);
+    L.Bpad = round_up(B_total > 0 ? B_total : 1, kSubCols);
+    L.n_row_tiles = (int)ceil_div(n_rows > 0 ? n_rows : 1, kTileRows);
+    L.S = (int)(L.Bpad / kSubCols);
+    L.n_rr = (int64_t)R * L.n_row_tiles;
+    L.F = L.n_rr * L.S;
+    // the larger occupancy of the two kernel variants bounds the slot count for both
+    const int per_sm = 8;
+    int64_t G = (int64_t)sm_count * per_sm;
+    if (G > L.F) G = L.F;
+    L.G_max = (int)(G > 0 ? G : 1);
+    L.max_segs = (int)(L.G_max / L.n_rr + 2);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    L.off_keys = take(sizeof(unsigned long long) * (size_t)R * L.N);
+    L.off_Us = take(sizeof(float) * (size_t)R * L.Bpad);
+    L.off_As = take(sizeof(float) * (size_t)R * L.Bpad);
+    L.off_Es = take(sizeof(float) * (size_t)R * L.Bpad);
+    L.off_perm = take(sizeof(int) * (size_t)R * L.Bpad);
+    L.off_rowpos = take(sizeof(int) * (size_t)R * (n_rows > 0 ? n_rows : 1));
+    L.off_flags = take(sizeof(int) * ARVAE_MAX_REG_DIMS);
+    L.off_pgrad = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
+    L.off_prow = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
+    L.off_lossp = take(sizeof(double) * (size_t)L.G_max);
+    L.bytes = off;
+    return L;
+}
+
+int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStream_t st) {
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + L.off_keys);
+    float *Xs = reinterpret_cast<float *>(ws + L.off_Us);
+    float *As = reinterpret_cast<float *>(ws + L.off_As);
+    float *Es = reinterpret_cast<float *>(ws + L.off_Es);
+    int *perm = reinterpret_cast<int *>(ws + L.off_perm);
+    int *rowpos = reinterpret_cast<int *>(ws + L.off_rowpos);
+    int *flags = reinterpret_cast<int *>(ws + L.off_flags);
+    const int64_t n_rows = P.row_end - P.row_begin;
+    const bool want_grad = P.grad_cols_out != nullptr;
+    const bool all_rows = (P.row_begin == 0 && P.row_end == P.B);
+
+    int rc = run_sort_keys(P.lab, P.lrs, P.lcs, P.dims, P.R, P.B, L.N, keys, st);
+    if (rc) return rc;
+    ARVAE_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ARVAE_MAX_REG_DIMS, st));
+    const double c = 2.0 * (double)P.factor * 1.4426950408889634074;  // 2 f log2(e)
+    const float fsign = P.factor > 0.f ? 1.0f : (P.factor < 0.f ? -1.0f : 0.0f);
+    const float cabs = P.factor != 0.f ? (float)fabs(c) : 1.0f;  // f == 0: xs == 0, any scale works
+    dim3 gg((unsigned)ceil_div(L.Bpad, 256), (unsigned)P.R);
+    sorted_gather_kernel<<<gg, 256, 0, st>>>(keys, L.N, P.z, P.zrs, P.zcs, P.lab, P.lrs, P.lcs, P.dims,
+                                             P.B, L.Bpad, fsign, cabs, Xs, As, Es, perm, flags);
+    ARVAE_LAUNCH_CHECK("sorted_gather_kernel");
+    if (!all_rows && n_rows > 0) {
+        row_select_kernel<<<P.R, 1024, 0, st>>>(perm, P.B, L.Bpad, P.row_begin, P.row_end, n_rows, rowpos);
+        ARVAE_LAUNCH_CHECK("row_select_kernel");
+    }
+
+    TilesArgs a;
+    a.Xs = Xs; a.Es = Es; a.As = As;
+    a.cabs = cabs;
+    a.rowpos = all_rows ? nullptr : rowpos;
+    a.flags = flags;
+    a.Bpad = L.Bpad; a.n_rows = n_rows;
+    a.n_row_tiles = L.n_row_tiles; a.S = L.S; a.F = L.F; a.n_rr = L.n_rr;
+    int64_t G = (int64_t)sm_count() * tiles_ctas_per_sm(want_grad);
+    if (G > L.G_max) G = L.G_max;
+    if (G < 1) G = 1;
+    a.G = (int)G;
+    a.force_general = 0;
+    a.pgrad = reinterpret_cast<double *>(ws + L.off_pgrad);
+    a.prow = P.row_loss_out ? reinterpret_cast<double *>(ws + L.off_prow) : nullptr;
+    a.lossp = reinterpret_cast<double *>(ws + L.off_lossp);
+
+    if (n_rows > 0) {
+        profile_begin(st);
+        if (want_grad) reg_tiles_kernel<true><<<a.G, kTileThreads, 0, st>>>(a);
+        else reg_tiles_kernel<false><<<a.G, kTileThreads, 0, st>>>(a);
+        profile_end(st);
+        ARVAE_LAUNCH_CHECK("reg_tiles_kernel");
+    } else {
+        a.G = 0;
+    }
+
+    const double BB = (double)P.B * (double)P.B;
+    const double lscale = (double)P.gamma / BB;
+    const double gscale = 8.0 * (double)P.gamma * (double)P.factor / BB;
+    const double pad_per_row = (double)(L.Bpad - P.B);
+    const int64_t work = n_rows * P.R;
+    reg_tiles_epilogue_kernel<<<(unsigned)(work > 0 ? ceil_div(work, 256) : 1), 256, 0, st>>>(
+        a, perm, P.R, P.row_begin, gscale, lscale, pad_per_row, P.grad_cols_out, P.row_loss_out,
+        P.loss_out, P.loss_f32_out);
+    ARVAE_LAUNCH_CHECK("reg_tiles_epilogue_kernel");
+    return 0;
+}
+
+}  // namespace arvae

@@ -29,6 +29,7 @@ import torch
 from . import _lib
 
 ALGO_AUTO, ALGO_DENSE, ALGO_SORTED = _lib.ALGO_AUTO, _lib.ALGO_DENSE, _lib.ALGO_SORTED
+HAVE_SORTED = True
 
 _EXACT_IN_F32 = (torch.float32, torch.float16, torch.bfloat16, torch.int8, torch.uint8, torch.int16,
                  torch.bool)
@@ -233,6 +234,31 @@ def reg_loss_rows(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int]
                                                  int(row_begin), int(row_end), want_grad, int(algo),
                                                  want_row_loss)
     return loss64, grad_cols, row_loss
+
+
+def mufu_per_pair(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], gamma, factor,
+                  algo: int = ALGO_AUTO) -> Tuple[float, ...]:
+    """MUFU instructions per evaluated pair, per regularised dim, that the kernels use on these inputs:
+    1 when the attribute-sorted path runs the factorised tanh (range guard |2 f log2(e) z| <= 62 holds
+    for the whole column), else 2.  Runs one forward to find out (roofline bookkeeping for bench.py)."""
+    _require_cuda_f32(z, "z")
+    dims = _normalize_dims(reg_dims, z.shape[1])
+    lab, lcols = _prepare_labels(labels, dims, z.shape[0], z.device)
+    lib = _lib.load()
+    B, R = z.shape[0], len(dims)
+    with torch.cuda.device(z.device):
+        loss64 = torch.empty((), dtype=torch.float64, device=z.device)
+        ws = torch.empty(max(int(lib.arvae_reg_loss_workspace_bytes(B, B, R)), 256), dtype=torch.uint8, device=z.device)
+        rc = lib.arvae_reg_loss_fwdbwd_f32(_ptr(z), z.stride(0), z.stride(1), _ptr(lab), lab.stride(0), lab.stride(1),
+                                           _lib.i32_array(dims), _lib.i32_array(lcols), R, 0, B, B, _scalar(gamma),
+                                           _scalar(factor), int(algo), _ptr(loss64), None, None, None, _ptr(ws),
+                                           ws.numel(), _stream(z.device))
+        _lib.check(rc, "arvae_reg_loss_fwdbwd_f32")
+        flags = (ctypes.c_int32 * R)()
+        rc = lib.arvae_reg_loss_path_flags(B, B, R, int(algo), _ptr(ws), flags, _stream(z.device))
+        if rc != 0:
+            return tuple(2.0 for _ in range(R))
+    return tuple(2.0 if f else 1.0 for f in flags)
 
 
 def sign_matrix(attribute: torch.Tensor) -> torch.Tensor:

@@ -35,7 +35,9 @@ import torch  # noqa: E402
 
 WORKLOAD = "c4_mnist_b65536"
 MUFU_LANES_PER_CLK_SM = 16.0     # sm_100 MUFU issue rate; confirmed by bench_tools/pipe_rates.cu (profiles/)
-MUFU_PER_PAIR = 2.0              # EX2 + RCP: cheapest tanh that meets the 1e-5 gate
+# MUFU per evaluated pair: 2 (EX2 + RCP on the latent difference, SURVEY App. B's cheapest admissible
+# dense form) on the dense path; 1 (RCP only, E_j/(E_i+E_j) with E = 2^u precomputed per element) where
+# the attribute-sorted path's range guard holds.  Measured per run via arvae_b200.mufu_per_pair().
 ALGO_BYTES_PER_ROWCOL = 4        # float32 per latent / label / gradient element
 
 
@@ -323,7 +325,10 @@ def main():
     peaks, peaks_src = load_peaks()
     sm_count = lib.arvae_device_sm_count()
     f_ghz = float(peaks.get("sm_max_mhz", 1965.0)) / 1e3
+    per_dim = arvae_b200.mufu_per_pair(case["z"].to(dev), case["labels"].to(dev), dims, gamma, delta, algo=args.algo)
+    MUFU_PER_PAIR = sum(per_dim) / len(per_dim)
     mufu_peak = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / MUFU_PER_PAIR  # Gpairs/s per GPU
+    mufu_peak_2 = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / 2.0
     k_ms = (ksum.value / kn.value) if kn.value else ms_step
     pairs_per_launch = pairs / world  # this rank's rows x all columns x R
     achieved = pairs_per_launch / (k_ms * 1e-3) / 1e9
@@ -332,8 +337,11 @@ def main():
         "bound": "mufu", "achieved": achieved, "peak": mufu_peak, "unit": "Gpairs/s", "frac": achieved / mufu_peak,
         "traffic": None,
         "peak_source": f"{MUFU_LANES_PER_CLK_SM:.0f} MUFU lanes/clk/SM x {sm_count} SMs x {f_ghz:.3f} GHz (sm_max_mhz, "
-                       f"MEASURED_PEAKS.json {peaks_src}) / {MUFU_PER_PAIR:.0f} MUFU per evaluated pair; "
+                       f"MEASURED_PEAKS.json {peaks_src}) / {MUFU_PER_PAIR:.2f} MUFU per evaluated pair (this run's "
+                       "algorithm; every one of the B^2 R ordered pairs is evaluated); "
                        "lane rate confirmed by bench_tools/pipe_rates.cu (profiles/)",
+        "frac_of_2mufu_dense_roof": achieved / mufu_peak_2, "peak_2mufu_dense": mufu_peak_2,
+        "mufu_per_pair_by_dim": list(per_dim),
         "kernel": "reg pair kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
         "evaluated_pairs_per_launch": pairs_per_launch, "mufu_per_pair": MUFU_PER_PAIR,
         "algorithmic_bytes_per_launch": algo_bytes,

@@ -96,6 +96,16 @@ ARVAE_API int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride
                               void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /*
+ * Which tanh form the attribute-sorted path used per dim in the call that last wrote `workspace_dev`
+ * (same B_total / n_rows / R): flags_out_host[r] = 0 -> 1 MUFU per pair (factorised E_j/(E_i+E_j)),
+ * 1 -> 2 MUFU per pair (range guard tripped: some |2 f log2(e) x| > 62).  Synchronises `stream`.
+ * Returns ARVAE_E_BADARG when the shape selects the dense path under `algo` (always 2 MUFU per pair).
+ */
+ARVAE_API int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_t algo,
+                                        const void *workspace_dev, int32_t *flags_out_host,
+                                        void *stream);
+
+/*
  * grad_z[k, :] = 0 ; grad_z[k, d_r] += grad_out * grad_cols[k, r]   for k in [0,n_rows)
  *   grad_out_dev [1] float (upstream gradient of the scalar loss) or NULL for 1.0
  *   grad_z_dev   [n_rows, Z] float with row stride gz_row_stride; every element is written.

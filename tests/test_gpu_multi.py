@@ -1,6 +1,8 @@
 """Row-block sharding on real GPUs (needs >= 2 devices; skipped otherwise): every world size gives
-the single-GPU loss, and each rank's gradient rows are BITWISE identical to the same rows of the
-single-GPU run (each row is owned by one rank and sweeps the same columns in the same order)."""
+the single-GPU loss and gradient.  On the dense path (B < 8192) each rank's gradient rows are BITWISE
+identical to the same rows of the single-GPU run (each row is owned by one rank and sweeps the same
+columns in the same order); on the attribute-sorted path the row tiles differ per partition, so
+equality holds to fp32 rounding (2e-6 of the column max)."""
 import os
 import sys
 
@@ -35,16 +37,16 @@ def _worker(rank, world, port, B, q):
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("B", [4096, 16384])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_equals_single_gpu(world):
+def test_sharded_equals_single_gpu(world, B):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import arvae_b200
     from arvae_b200 import synth
-    B = 8192
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + world
+    port = 29700 + (os.getpid() % 1000) + world + (B // 4096)
     procs = [ctx.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -60,4 +62,9 @@ def test_sharded_equals_single_gpu(world):
         assert r[1] == results[0][1]
         assert abs(r[1] - loss.item()) <= 1e-6 * abs(loss.item())
     got = np.concatenate([r[2] for r in results], axis=0)
-    assert np.array_equal(got, z.grad.cpu().numpy())
+    ref = z.grad.cpu().numpy()
+    if B < 8192:
+        assert np.array_equal(got, ref)
+    else:
+        scale = np.abs(ref).max(axis=0) + 1e-30
+        assert np.all(np.abs(got - ref).max(axis=0) <= 2e-6 * scale)

@@ -215,9 +215,16 @@ def test_row_blocks_add_up_and_rows_are_bitwise_identical(ab, algo):
         parts.append(l.item())
         grads.append(gc)
         rows.append(rl)
-    assert abs(sum(parts) - full_loss.item()) <= 1e-12 * abs(full_loss.item())
-    assert torch.equal(torch.cat(grads, 0), full_grad)  # each row sweeps the same columns in the same order
-    assert torch.equal(torch.cat(rows, 0), full_rows)
+    assert abs(sum(parts) - full_loss.item()) <= (1e-12 if algo == 1 else 1e-8) * abs(full_loss.item())
+    if algo == 1:
+        # dense path: each row sweeps the same columns in the same order whatever the row block
+        assert torch.equal(torch.cat(grads, 0), full_grad)
+        assert torch.equal(torch.cat(rows, 0), full_rows)
+    else:
+        # sorted path: the grouping of rows into tiles (hence the tile classes) depends on the row
+        # block, so equality holds to fp32 rounding of the partial sums, not bitwise
+        assert_grad_close(torch.cat(grads, 0).cpu().numpy(), full_grad.cpu().numpy(), 2e-6)
+        assert torch.allclose(torch.cat(rows, 0), full_rows, rtol=1e-6, atol=0)
     assert_loss_close(full_loss.item(), g["loss"])
     # per-row sums add up to the loss
     tot = full_rows.sum().item() * gamma / (B * B)
