@@ -8,7 +8,8 @@ from __future__ import annotations
 
 from . import _lib  # noqa: F401
 from .ops import (ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, compute_kld_loss, compute_reg_loss, latent_head, mufu_per_pair,
-                  reg_loss_fused, reg_loss_rows, reg_loss_sign, reparam_kld_reg, reparametrize, sign_matrix)
+                  reg_loss_fused, reg_loss_rows, reg_loss_sign, reparam_kld_reg, reparametrize, sign_matrix,
+                  attr_argsort, pack_columns)
 
 __version__ = "0.1.0"
 

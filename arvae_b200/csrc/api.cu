@@ -358,6 +358,45 @@ int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z, const flo
 
 void arvae_host_release(void) { g_host.release(); }
 
+int arvae_pack_columns_f32(const float *z_dev, int64_t z_row_stride, int64_t z_col_stride,
+                           const float *labels_dev, int64_t lab_row_stride, int64_t lab_col_stride,
+                           const int32_t *reg_dims_host, const int32_t *label_cols_host, int32_t R,
+                           int64_t n_rows, float *out_dev, void *stream) {
+    RegDims d;
+    int rc = fill_dims(d, reg_dims_host, label_cols_host, R);
+    if (rc) return rc;
+    if (n_rows < 0 || (n_rows * R > 0 && (!z_dev || !labels_dev || !out_dev))) {
+        set_error("bad argument to pack_columns");
+        return ARVAE_E_BADARG;
+    }
+    return run_pack_slice(z_dev, z_row_stride, z_col_stride, labels_dev, lab_row_stride, lab_col_stride, d, R,
+                          n_rows, out_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t arvae_attr_argsort_workspace_bytes(int64_t B) {
+    if (B < 0) return 0;
+    return sizeof(unsigned long long) * (size_t)sort_padded_size(B);
+}
+
+int arvae_attr_argsort_f32(const float *labels_dev, int64_t lab_stride, int64_t B, int32_t *perm_out_dev,
+                           void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (B < 0 || !workspace_dev || (B > 0 && (!labels_dev || !perm_out_dev))) {
+        set_error("bad argument to attr_argsort");
+        return ARVAE_E_BADARG;
+    }
+    if (workspace_bytes < arvae_attr_argsort_workspace_bytes(B)) {
+        set_error("workspace too small for attr_argsort");
+        return ARVAE_E_WORKSPACE;
+    }
+    RegDims d;
+    memset(&d, 0, sizeof(d));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(workspace_dev);
+    int rc = run_sort_keys(labels_dev, lab_stride, 1, d, 1, B, sort_padded_size(B), keys, st);
+    if (rc) return rc;
+    return run_extract_perm(keys, B, perm_out_dev, st);
+}
+
 int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
                              int8_t *out_dev, void *stream) {
     if (B < 0 || (B > 0 && (!labels_dev || !out_dev))) {

@@ -215,6 +215,24 @@ reg_scatter_bwd_kernel(const float *__restrict__ grad_cols, const float *__restr
 }
 
 __global__ void __launch_bounds__(256)
+pack_slice_kernel(const float *__restrict__ z, int64_t zrs, int64_t zcs, const float *__restrict__ lab,
+                  int64_t lrs, int64_t lcs, RegDims dims, int R, int64_t n_rows,
+                  float *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n_rows * 2R
+    if (idx >= n_rows * 2 * R) return;
+    const int64_t k = idx / (2 * R);
+    const int c = (int)(idx % (2 * R));
+    out[idx] = c < R ? __ldg(z + k * zrs + (int64_t)dims.zcol[c] * zcs)
+                     : __ldg(lab + k * lrs + (int64_t)dims.lcol[c - R] * lcs);
+}
+
+__global__ void __launch_bounds__(256)
+extract_perm_kernel(const unsigned long long *__restrict__ keys, int64_t B, int32_t *__restrict__ perm) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < B) perm[k] = (int32_t)(keys[k] & 0xFFFFFFFFull);
+}
+
+__global__ void __launch_bounds__(256)
 sign_matrix_kernel(const float *__restrict__ a, int64_t stride, int64_t B,
                    int8_t *__restrict__ out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,6 +337,22 @@ int run_scatter_bwd(const float *grad_cols, const float *grad_out, const RegDims
     reg_scatter_bwd_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, st>>>(grad_cols, grad_out, dims,
                                                                          R, n_rows, Z, grad_z, gzrs);
     ARVAE_LAUNCH_CHECK("reg_scatter_bwd_kernel");
+    return 0;
+}
+
+int run_pack_slice(const float *z, int64_t zrs, int64_t zcs, const float *lab, int64_t lrs, int64_t lcs,
+                   const RegDims &dims, int R, int64_t n_rows, float *out, cudaStream_t st) {
+    const int64_t work = n_rows * 2 * R;
+    if (work <= 0) return 0;
+    pack_slice_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, st>>>(z, zrs, zcs, lab, lrs, lcs, dims, R, n_rows, out);
+    ARVAE_LAUNCH_CHECK("pack_slice_kernel");
+    return 0;
+}
+
+int run_extract_perm(const unsigned long long *keys, int64_t B, int32_t *perm, cudaStream_t st) {
+    if (B <= 0) return 0;
+    extract_perm_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(keys, B, perm);
+    ARVAE_LAUNCH_CHECK("extract_perm_kernel");
     return 0;
 }
 

@@ -46,6 +46,9 @@ DenseLayout dense_layout(int64_t B_total, int64_t n_rows, int R, int sm_count);
 int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStream_t st);
 int run_scatter_bwd(const float *grad_cols, const float *grad_out, const RegDims &dims, int R,
                     int64_t n_rows, int64_t Z, float *grad_z, int64_t gzrs, cudaStream_t st);
+int run_pack_slice(const float *z, int64_t zrs, int64_t zcs, const float *lab, int64_t lrs, int64_t lcs,
+                   const RegDims &dims, int R, int64_t n_rows, float *out, cudaStream_t st);
+int run_extract_perm(const unsigned long long *keys, int64_t B, int32_t *perm, cudaStream_t st);
 int run_sign_matrix(const float *a, int64_t stride, int64_t B, int8_t *out, cudaStream_t st);
 
 // attribute-sorted path (sort.cu, reg_sorted.cu)

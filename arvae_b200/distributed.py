@@ -32,7 +32,9 @@ from . import ops
 def pack_columns(z_local: torch.Tensor, labels_local: torch.Tensor, reg_dims: Sequence[int],
                  label_cols: Sequence[int]) -> torch.Tensor:
     """[B_local, 2R] float32: the R regularised latent columns, then the R attribute columns."""
-    zc = z_local.detach()[:, list(reg_dims)]
+    if z_local.is_cuda and labels_local.dtype == torch.float32:
+        return ops.pack_columns(z_local.detach(), labels_local.detach(), reg_dims, label_cols)  # one launch
+    zc = z_local.detach()[:, list(reg_dims)]  # host-logic tests (gloo, CPU tensors) and exact-cast label dtypes
     lc = labels_local.detach()[:, list(label_cols)].to(torch.float32)
     return torch.cat([zc, lc], dim=1).contiguous()
 

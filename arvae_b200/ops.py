@@ -261,6 +261,36 @@ def mufu_per_pair(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int]
     return tuple(2.0 if f else 1.0 for f in flags)
 
 
+def attr_argsort(attribute: torch.Tensor) -> torch.Tensor:
+    """int32 [B] permutation that orders the attribute ascending (ties by index, NaN last) -- the order
+    the attribute-sorted pair kernel works in (bitonic sort of csrc/sort.cu; parity tests)."""
+    lab, _ = _prepare_labels(attribute.reshape(-1), (0,), attribute.numel(), attribute.device)
+    B = lab.shape[0]
+    lib = _lib.load()
+    with torch.cuda.device(lab.device):
+        perm = torch.empty(B, dtype=torch.int32, device=lab.device)
+        ws = torch.empty(max(int(lib.arvae_attr_argsort_workspace_bytes(B)), 256), dtype=torch.uint8, device=lab.device)
+        rc = lib.arvae_attr_argsort_f32(_ptr(lab), lab.stride(0), B, _ptr(perm), _ptr(ws), ws.numel(),
+                                        _stream(lab.device))
+        _lib.check(rc, "arvae_attr_argsort_f32")
+    return perm
+
+
+def pack_columns(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], label_cols: Sequence[int]) -> torch.Tensor:
+    """[n, 2R] float32 = the regularised latent columns then the attribute columns of these rows (one launch);
+    the slice a rank contributes to the column all-gather of the row-block sharded loss."""
+    _require_cuda_f32(z, "z")
+    _require_cuda_f32(labels, "labels")
+    n, R = z.shape[0], len(reg_dims)
+    with torch.cuda.device(z.device):
+        out = torch.empty((n, 2 * R), dtype=torch.float32, device=z.device)
+        rc = _lib.load().arvae_pack_columns_f32(_ptr(z), z.stride(0), z.stride(1), _ptr(labels), labels.stride(0),
+                                                labels.stride(1), _lib.i32_array(reg_dims), _lib.i32_array(label_cols),
+                                                R, n, _ptr(out), _stream(z.device))
+        _lib.check(rc, "arvae_pack_columns_f32")
+    return out
+
+
 def sign_matrix(attribute: torch.Tensor) -> torch.Tensor:
     """int8 [B,B] sign(a_i - a_j) from the same compare the pair kernels use (parity tests)."""
     lab, _ = _prepare_labels(attribute.reshape(-1), (0,), attribute.numel(), attribute.device)

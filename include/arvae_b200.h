@@ -162,6 +162,25 @@ ARVAE_API int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z,
                             void *stream);
 ARVAE_API void arvae_host_release(void);
 
+/*
+ * Row-block sharding helper: out[k, 0:R] = z[k, d_r], out[k, R:2R] = labels[k, c_r] for k in [0,n_rows)
+ * -- the packed [n_rows, 2R] float slice each rank contributes to the all-gather of columns.
+ */
+ARVAE_API int arvae_pack_columns_f32(const float *z_dev, int64_t z_row_stride, int64_t z_col_stride,
+                                     const float *labels_dev, int64_t lab_row_stride,
+                                     int64_t lab_col_stride, const int32_t *reg_dims_host,
+                                     const int32_t *label_cols_host, int32_t R, int64_t n_rows,
+                                     float *out_dev, void *stream);
+
+/*
+ * perm_out_dev[k] = index of the k-th smallest attribute (ties by index, NaN last): the order the
+ * attribute-sorted path uses.  workspace: arvae_attr_argsort_workspace_bytes(B) bytes.  (parity tests)
+ */
+ARVAE_API size_t arvae_attr_argsort_workspace_bytes(int64_t B);
+ARVAE_API int arvae_attr_argsort_f32(const float *labels_dev, int64_t lab_stride, int64_t B,
+                                     int32_t *perm_out_dev, void *workspace_dev,
+                                     size_t workspace_bytes, void *stream);
+
 /* s[i*B+j] = sign(a_i - a_j) as int8, for parity tests at small B (same compare the kernels use). */
 ARVAE_API int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
                              int8_t *out_dev, void *stream);

@@ -393,3 +393,59 @@ def test_host_buffer_entry_point(ab):
     assert_loss_close(loss.value, g["loss"])
     assert_grad_close(grad, g["grad_z"])
     lib.arvae_host_release()
+
+
+# ------------------------------------------------------------------------------------------------
+# building blocks of the attribute-sorted path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 2, 255, 256, 257, 5000, 8192, 8193, 40000, 65536, 150000])
+def test_attr_argsort_matches_stable_sort(ab, B):
+    """Sortedness + permutation property at every size class of the bitonic network (single chunk,
+    1/2/3 fused global steps), with ties, NaN, +-inf and +-0 in the keys."""
+    g = torch.Generator().manual_seed(B)
+    a = torch.randint(-50, 50, (B,), generator=g).float() / 7.0 if B % 2 else torch.randn(B, generator=g)
+    if B > 20:
+        a[3] = float("nan"); a[7] = float("inf"); a[11] = float("-inf"); a[13] = 0.0; a[17] = -0.0; a[19] = float("nan")
+    perm = ab.attr_argsort(a.cuda()).cpu().long()
+    assert sorted(perm.tolist()) == list(range(B))            # a permutation
+    s = a[perm]
+    nan = torch.isnan(s)
+    n_nan = int(nan.sum())
+    assert not nan[:B - n_nan].any() and nan[B - n_nan:].all()  # NaN last
+    v = s[:B - n_nan]
+    assert bool((v[1:] >= v[:-1]).all())                       # ascending
+    # ties (incl. -0 / +0 which compare equal but have distinct keys) keep a deterministic order:
+    # equal BIT patterns come out by increasing original index
+    bits = a.view(torch.int32)[perm]
+    same = bits[1:] == bits[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())
+
+
+def test_pack_columns(ab):
+    z = torch.randn(300, 9, device="cuda")
+    lab = torch.randn(300, 5, device="cuda")
+    p = ab.pack_columns(z, lab, (1, 8, 3), (0, 4, 2))
+    ref = torch.cat([z[:, [1, 8, 3]], lab[:, [0, 4, 2]]], dim=1)
+    assert torch.equal(p, ref)
+    zt = torch.randn(9, 300, device="cuda").t()  # non-contiguous rows
+    assert torch.equal(ab.pack_columns(zt, lab, (2,), (1,)), torch.cat([zt[:, [2]], lab[:, [1]]], dim=1))
+
+
+def test_mufu_range_guard_falls_back_to_two_mufu_form(ab, oracle_mod):
+    """|2 f log2(e) z| > 62 somewhere in a column -> that dim uses EX2+RCP on the latent difference; results
+    must still match the oracle, and the dims inside the guard keep the 1-MUFU form."""
+    B = 9000
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn(B, 3, generator=g)
+    z[5, 1] = 30.0           # 2.885 * 30 > 62
+    labels = torch.randn(B, 3, generator=g)
+    per_dim = ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 1, 2), 1.0, 1.0)
+    assert per_dim == (1.0, 2.0, 1.0)
+    ref_loss, ref_grad = oracle_mod.compute_reg_loss_multi(z.numpy(), labels.numpy(), (0, 1, 2), 1.0, 1.0, f64=True)
+    zc = z.cuda().requires_grad_(True)
+    loss = ab.reg_loss_fused(zc, labels.cuda(), (0, 1, 2), 1.0, 1.0)
+    loss.backward()
+    assert_loss_close(loss.item(), ref_loss)
+    assert_grad_close(zc.grad.cpu().numpy(), ref_grad)
+    # delta = 10 (the MeasureVAE setting): every N(0,1) column trips the guard
+    assert set(ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 2), 1.0, 10.0)) == {2.0}
