@@ -58,7 +58,7 @@ struct SortedLayout {
     int n_row_tiles, S;
     int64_t n_rr, F;
     int G_max, max_segs;
-    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_pgrad, off_prow,
+    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_pgrad, off_prow,
         off_lossp, bytes;
 };
 int64_t sort_padded_size(int64_t B);

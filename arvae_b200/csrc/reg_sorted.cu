@@ -34,6 +34,7 @@ constexpr int kTileRI = 4;
 constexpr int kTileRows = kTileThreads * kTileRI;  // 512 rows per row tile
 constexpr int kStageCols = 2048;                   // columns staged per __syncthreads pair
 constexpr float kMufu1MaxAbsU = 62.0f;
+static_assert(kTileRows / (kTileThreads / 32) == kTileRI * 32, "a warp owns kTileRI x 32 consecutive rows");
 
 // ------------------------------------------------------------------------------------------------
 // gather the sorted order: Us/As/Es[r][k] for sorted position k, perm[r][k] = original index
@@ -44,9 +45,15 @@ sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
                      const float *__restrict__ lab, int64_t lrs, int64_t lcs, RegDims dims,
                      int64_t B, int64_t Bpad, float fsign, float cabs, float *__restrict__ Xs,
                      float *__restrict__ As, float *__restrict__ Es, int *__restrict__ perm,
-                     int *__restrict__ flags) {
+                     int *__restrict__ flags, int64_t row_begin, int64_t row_end,
+                     int *__restrict__ blockcnt) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
+    int mine = 0;
+    if (k < B) mine = ((int64_t)(unsigned int)(keys[(int64_t)r * N + k] & 0xFFFFFFFFull) >= row_begin &&
+                       (int64_t)(unsigned int)(keys[(int64_t)r * N + k] & 0xFFFFFFFFull) < row_end);
+    const int cnt = __syncthreads_count(mine);  // rows of this call among this CTA's 256 sorted positions
+    if (blockcnt && threadIdx.x == 0) blockcnt[(int64_t)r * gridDim.x + blockIdx.x] = cnt;
     if (k >= Bpad) return;
     const int64_t o = (int64_t)r * Bpad + k;
     if (k < B) {
@@ -67,29 +74,41 @@ sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
 }
 
 // rowpos[r][m] = m-th sorted position whose original index lies in [row_begin,row_end)
-// (row-block sharding: this rank's rows, in attribute order).  One CTA per dim.
+// (row-block sharding: this rank's rows, in attribute order).  Order-preserving compaction: the gather
+// kernel left per-256-position counts; CTA b of dim r sums the counts before its 1024 positions and
+// ranks its own positions with ballots.
 __global__ void __launch_bounds__(1024)
-row_select_kernel(const int *__restrict__ perm, int64_t B, int64_t Bpad, int64_t row_begin,
-                  int64_t row_end, int64_t n_rows, int *__restrict__ rowpos) {
-    __shared__ int scount[1024];
-    const int r = blockIdx.x;
-    const int *p = perm + (int64_t)r * Bpad;
-    const int64_t per = ceil((double)B / 1024.0);
-    const int64_t k0 = min((int64_t)threadIdx.x * per, B), k1 = min(k0 + per, B);
-    int cnt = 0;
-    for (int64_t k = k0; k < k1; ++k) cnt += (p[k] >= row_begin && p[k] < row_end);
-    scount[threadIdx.x] = cnt;
+row_select_kernel(const int *__restrict__ perm, const int *__restrict__ blockcnt, int n_cnt, int64_t B,
+                  int64_t Bpad, int64_t row_begin, int64_t row_end, int64_t n_rows,
+                  int *__restrict__ rowpos) {
+    __shared__ int swarp[32];
+    __shared__ int sbase;
+    const int r = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int *cnt = blockcnt + (int64_t)r * n_cnt;
+    int part = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x * 4 && i < n_cnt; i += 1024) part += cnt[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) swarp[warp] = part;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan
-        const int v = threadIdx.x >= o ? scount[threadIdx.x - o] : 0;
-        __syncthreads();
-        scount[threadIdx.x] += v;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += swarp[w];
+        sbase = t;
     }
-    int64_t m = scount[threadIdx.x] - cnt;
-    int *out = rowpos + (int64_t)r * n_rows;
-    for (int64_t k = k0; k < k1; ++k)
-        if (p[k] >= row_begin && p[k] < row_end) out[m++] = (int)k;
+    __syncthreads();
+    const int base = sbase;
+    const int64_t k = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int v = k < B ? perm[(int64_t)r * Bpad + k] : -1;
+    const bool f = v >= row_begin && v < row_end;
+    const unsigned int b = __ballot_sync(0xffffffffu, f);
+    __syncthreads();
+    if (lane == 0) swarp[warp] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += swarp[w];
+    if (f) rowpos[(int64_t)r * n_rows + base + before + __popc(b & ((1u << lane) - 1u))] = (int)k;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -251,6 +270,7 @@ struct TilesArgs {
     const int *flags;           // [R] non-zero: some |u| > 62, use the 2-MUFU form for this dim
     int64_t Bpad, n_rows;
     int n_row_tiles, S;         // S = Bpad / kSubCols sub-chunks per row tile
+    int P;                      // sub-chunk visiting stride (coprime to S)
     int64_t F;                  // fine units = R * n_row_tiles * S
     int G;                      // persistent CTAs
     int64_t n_rr;               // R * n_row_tiles
@@ -297,17 +317,22 @@ reg_tiles_kernel(TilesArgs a) {
         const float *Ar = a.As + (int64_t)r * a.Bpad;
         const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
 
-        const int64_t m0 = (int64_t)I * kTileRows;
-        const int64_t mlast = min(m0 + kTileRows, a.n_rows) - 1;
-        const float amin = Ar[rp ? rp[m0] : m0];
-        const float amax = Ar[rp ? rp[mlast] : mlast];
+        // Each warp owns 128 CONSECUTIVE sorted rows of the tile (lane l, k -> row 128 w + 32 k + l) and
+        // classifies sub-chunks against ITS OWN attribute range: the general band a warp sees is as wide
+        // as 128 rows, not 512 (matters most for row-block shards, whose rows are 1/G of the columns).
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int64_t m0 = (int64_t)I * kTileRows + (int64_t)warp * (kTileRows / (kTileThreads / 32));
+        const int64_t mlast = min(m0 + kTileRows / (kTileThreads / 32), a.n_rows) - 1;
+        const bool warp_has_rows = m0 < a.n_rows;
+        const float amin = warp_has_rows ? Ar[rp ? rp[m0] : m0] : 0.0f;
+        const float amax = warp_has_rows ? Ar[rp ? rp[mlast] : mlast] : 0.0f;
 
         RowRegs R;
         bool valid[kTileRI];
         double dl[kTileRI], dg[kTileRI];
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
-            const int64_t m = m0 + threadIdx.x + (int64_t)k * kTileThreads;
+            const int64_t m = m0 + (int64_t)k * 32 + lane;
             valid[k] = m < a.n_rows;
             const int64_t pos = valid[k] ? (rp ? (int64_t)rp[m] : m) : 0;
             R.e[k] = valid[k] ? Er[pos] : 1.0f;
@@ -317,17 +342,23 @@ reg_tiles_kernel(TilesArgs a) {
             dg[k] = 0.0;
         }
 
-        const int64_t col_end = (int64_t)s1 * kSubCols;
-        for (int64_t cs = (int64_t)s0 * kSubCols; cs < col_end; cs += kStageCols) {
-            const int n = (int)min((int64_t)kStageCols, col_end - cs);
+        // Sub-chunks are visited in a permuted order, s = (s' * P) mod S with P ~ 0.618 S coprime to S:
+        // any contiguous range of s' is spread evenly over the columns, so every CTA sees the same mix of
+        // cheap constant-sign tiles and expensive general / tie tiles (the general band of a row tile is
+        // contiguous in s and would otherwise land on a few CTAs).
+        constexpr int kStageSubs = kStageCols / kSubCols;
+        for (int sp = s0; sp < s1; sp += kStageSubs) {
+            const int nsub = min(kStageSubs, s1 - sp);
             __syncthreads();
-            for (int q = threadIdx.x * 4; q < n; q += kTileThreads * 4) {
-                *reinterpret_cast<float4 *>(se + q) = *reinterpret_cast<const float4 *>(Er + cs + q);
-                *reinterpret_cast<float4 *>(sx + q) = *reinterpret_cast<const float4 *>(Xr + cs + q);
-                *reinterpret_cast<float4 *>(sa + q) = *reinterpret_cast<const float4 *>(Ar + cs + q);
+            for (int q = threadIdx.x * 4; q < nsub * kSubCols; q += kTileThreads * 4) {
+                const int w = q / kSubCols;
+                const int64_t col = (((int64_t)(sp + w) * a.P) % a.S) * kSubCols + (q - w * kSubCols);
+                *reinterpret_cast<float4 *>(se + q) = *reinterpret_cast<const float4 *>(Er + col);
+                *reinterpret_cast<float4 *>(sx + q) = *reinterpret_cast<const float4 *>(Xr + col);
+                *reinterpret_cast<float4 *>(sa + q) = *reinterpret_cast<const float4 *>(Ar + col);
             }
             __syncthreads();
-            for (int sub = 0; sub < n; sub += kSubCols) {
+            for (int sub = 0; sub < nsub * kSubCols; sub += kSubCols) {
                 const int cls = a.force_general ? (int)kClassGeneral
                                                 : classify(amin, amax, sa[sub], sa[sub + kSubCols - 1]);
                 if (mufu1) sweep_subchunk<true, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
@@ -340,7 +371,7 @@ reg_tiles_kernel(TilesArgs a) {
         const int64_t slot = (seg * a.n_rr + rr) * kTileRows;
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
-            const int64_t o = slot + threadIdx.x + (int64_t)k * kTileThreads;
+            const int64_t o = slot + warp * (kTileRows / (kTileThreads / 32)) + k * 32 + lane;  // = row - tile start
             if (valid[k]) lthread += dl[k];
             if (GRAD) a.pgrad[o] = dg[k];
             if (a.prow) a.prow[o] = dl[k];
@@ -406,6 +437,18 @@ reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int6
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int golden_stride(int S) {  // integer nearest 0.618 S that is coprime to S
+    if (S <= 2) return 1;
+    auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };
+    int p = (int)(0.6180339887 * S + 0.5);
+    if (p < 1) p = 1;
+    for (int d = 0; d < S; ++d) {
+        if (p + d < S && gcd(p + d, S) == 1) return p + d;
+        if (p - d >= 1 && gcd(p - d, S) == 1) return p - d;
+    }
+    return 1;
+}
+
 static int tiles_ctas_per_sm(bool grad) {
     static int cache[2] = {0, 0};
     int &v = cache[grad ? 1 : 0];
@@ -449,6 +492,7 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count)
     L.off_perm = take(sizeof(int) * (size_t)R * L.Bpad);
     L.off_rowpos = take(sizeof(int) * (size_t)R * (n_rows > 0 ? n_rows : 1));
     L.off_flags = take(sizeof(int) * ARVAE_MAX_REG_DIMS);
+    L.off_blockcnt = take(sizeof(int) * (size_t)R * (size_t)ceil_div(L.Bpad, 256));
     L.off_pgrad = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
     L.off_prow = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
     L.off_lossp = take(sizeof(double) * (size_t)L.G_max);
@@ -464,6 +508,7 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     int *perm = reinterpret_cast<int *>(ws + L.off_perm);
     int *rowpos = reinterpret_cast<int *>(ws + L.off_rowpos);
     int *flags = reinterpret_cast<int *>(ws + L.off_flags);
+    int *blockcnt = reinterpret_cast<int *>(ws + L.off_blockcnt);
     const int64_t n_rows = P.row_end - P.row_begin;
     const bool want_grad = P.grad_cols_out != nullptr;
     const bool all_rows = (P.row_begin == 0 && P.row_end == P.B);
@@ -476,10 +521,13 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     const float cabs = P.factor != 0.f ? (float)fabs(c) : 1.0f;  // f == 0: xs == 0, any scale works
     dim3 gg((unsigned)ceil_div(L.Bpad, 256), (unsigned)P.R);
     sorted_gather_kernel<<<gg, 256, 0, st>>>(keys, L.N, P.z, P.zrs, P.zcs, P.lab, P.lrs, P.lcs, P.dims,
-                                             P.B, L.Bpad, fsign, cabs, Xs, As, Es, perm, flags);
+                                             P.B, L.Bpad, fsign, cabs, Xs, As, Es, perm, flags,
+                                             P.row_begin, P.row_end, all_rows ? nullptr : blockcnt);
     ARVAE_LAUNCH_CHECK("sorted_gather_kernel");
     if (!all_rows && n_rows > 0) {
-        row_select_kernel<<<P.R, 1024, 0, st>>>(perm, P.B, L.Bpad, P.row_begin, P.row_end, n_rows, rowpos);
+        dim3 gs((unsigned)ceil_div(L.Bpad, 1024), (unsigned)P.R);
+        row_select_kernel<<<gs, 1024, 0, st>>>(perm, blockcnt, (int)gg.x, P.B, L.Bpad, P.row_begin, P.row_end,
+                                               n_rows, rowpos);
         ARVAE_LAUNCH_CHECK("row_select_kernel");
     }
 
@@ -490,6 +538,7 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     a.flags = flags;
     a.Bpad = L.Bpad; a.n_rows = n_rows;
     a.n_row_tiles = L.n_row_tiles; a.S = L.S; a.F = L.F; a.n_rr = L.n_rr;
+    a.P = golden_stride(L.S);
     int64_t G = (int64_t)sm_count() * tiles_ctas_per_sm(want_grad);
     if (G > L.G_max) G = L.G_max;
     if (G < 1) G = 1;

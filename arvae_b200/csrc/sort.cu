@@ -10,8 +10,9 @@
 
 namespace arvae {
 
-constexpr int kSortChunk = 8192;    // keys sorted per CTA in (dynamic) shared memory: 64 KiB
-constexpr int kSortThreads = 1024;  // each thread owns kSortChunk / kSortThreads / 2 compare-exchanges per step
+constexpr int kSortChunk = 4096;   // keys sorted per CTA in shared memory (32 KiB): small enough that a
+                                   // 65536-key x 6-dim sort spreads over 96 CTAs
+constexpr int kSortThreads = 512;  // 8 keys per thread
 
 __device__ __forceinline__ unsigned int float_to_sortable(float a) {
     if (a != a) return 0xFFFFFFFEu;  // every NaN: one class, after +inf (0xFF800000)
@@ -41,6 +42,91 @@ __device__ __forceinline__ void cmpx(unsigned long long &a, unsigned long long &
     }
 }
 
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int mask) {
+    const unsigned int lo = __shfl_xor_sync(0xffffffffu, (unsigned int)v, mask);
+    const unsigned int hi = __shfl_xor_sync(0xffffffffu, (unsigned int)(v >> 32), mask);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// Shared-memory round with STEPS (1..3) partner distances j, j/2, .. >= 256: each thread owns the 2^STEPS
+// keys that differ only in those bits (lanes stay consecutive in the low index bits: no bank conflicts).
+template <int STEPS>
+__device__ __forceinline__ void smem_round_strided(unsigned long long *s, int n, int64_t g0, int64_t k, int j) {
+    constexpr int E = 1 << STEPS;
+    const int jl = j >> (STEPS - 1);
+    for (int t = threadIdx.x; t < (n >> STEPS); t += kSortThreads) {
+        const int i0 = ((t & ~(jl - 1)) << STEPS) | (t & (jl - 1));
+        const bool asc = (((g0 + i0) & k) == 0);
+        unsigned long long v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = s[i0 + m * jl];
+#pragma unroll
+        for (int st = STEPS - 1; st >= 0; --st)
+#pragma unroll
+            for (int m = 0; m < E; ++m)
+                if ((m & (1 << st)) == 0) cmpx(v[m], v[m | (1 << st)], asc);
+#pragma unroll
+        for (int m = 0; m < E; ++m) s[i0 + m * jl] = v[m];
+    }
+}
+
+// Tail round: every step with partner distance <= 128 of stages k_first .. k_last, without touching
+// shared memory in between.  A thread owns 8 keys at i0 + 32 m (distances 32/64/128 are register pairs),
+// a warp owns 256 consecutive keys (distances 16..1 are lane exchanges by shuffle).
+__device__ __forceinline__ void smem_round_tail(unsigned long long *s, int n, int64_t g0, int64_t k_first,
+                                                int64_t k_last) {
+    const int lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < (n >> 3); t += kSortThreads) {  // n >= 256: whole warps stay together
+        const int i0 = ((t >> 5) << 8) | lane;
+        unsigned long long v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = s[i0 + 32 * m];
+        for (int64_t k = k_first; k <= k_last; k <<= 1) {
+            const int jtop = (int)min((int64_t)128, k >> 1);
+            for (int j = jtop; j >= 32; j >>= 1) {
+                const int mb = j >> 5;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    if ((m & mb) == 0) {
+                        const bool asc = (((g0 + i0 + 32 * m) & k) == 0);
+                        // register indices must be compile-time: enumerate the three possible partners
+                        if (mb == 1) cmpx(v[m], v[m | 1], asc);
+                        else if (mb == 2) cmpx(v[m], v[m | 2], asc);
+                        else cmpx(v[m], v[m | 4], asc);
+                    }
+                }
+            }
+            for (int j = min(jtop, 16); j >= 1; j >>= 1) {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const unsigned long long o = shfl_xor_u64(v[m], j);
+                    const bool asc = (((g0 + i0 + 32 * m) & k) == 0);
+                    const bool keep_min = (lower == asc);
+                    v[m] = keep_min ? (v[m] < o ? v[m] : o) : (v[m] > o ? v[m] : o);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) s[i0 + 32 * m] = v[m];
+    }
+}
+
+// Steps of stage k with partner distance from j_top down to 256, in strided rounds of <= 3 steps.
+__device__ __forceinline__ void smem_steps_down_to_256(unsigned long long *s, int n, int64_t g0, int64_t k,
+                                                       int j_top) {
+    int j = j_top;
+    while (j >= 256) {
+        int steps = 0;
+        for (int jj = j; jj >= 256 && steps < 3; jj >>= 1) ++steps;
+        if (steps == 3) smem_round_strided<3>(s, n, g0, k, j);
+        else if (steps == 2) smem_round_strided<2>(s, n, g0, k, j);
+        else smem_round_strided<1>(s, n, g0, k, j);
+        __syncthreads();
+        j >>= steps;
+    }
+}
+
 // Sorts each kSortChunk-sized chunk in shared memory: all stages with k <= kSortChunk when
 // `k_only` == 0, or only the tail j = kSortChunk/2 .. 1 of stage `k_only` when merging.
 __global__ void __launch_bounds__(kSortThreads)
@@ -48,21 +134,21 @@ bitonic_local_kernel(unsigned long long *__restrict__ keys, int64_t N, int64_t k
     extern __shared__ __align__(16) unsigned long long s[];
     unsigned long long *base = keys + (int64_t)blockIdx.y * N + (int64_t)blockIdx.x * kSortChunk;
     const int64_t g0 = (int64_t)blockIdx.x * kSortChunk;  // global index of s[0] within this dim
-    const int n = (int)min((int64_t)kSortChunk, N);       // N is a power of two
+    const int n = (int)min((int64_t)kSortChunk, N);       // N is a power of two >= 256
     for (int i = threadIdx.x; i < n; i += kSortThreads) s[i] = base[i];
     __syncthreads();
-    const int64_t k_begin = k_only ? k_only : 2;
-    const int64_t k_end = k_only ? k_only : n;
-    for (int64_t k = k_begin; k <= k_end; k <<= 1) {
-        int j0 = (int)min((int64_t)(n >> 1), k >> 1);
-        for (int j = j0; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n >> 1); t += kSortThreads) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
-                const bool asc = (((g0 + i) & k) == 0);
-                cmpx(s[i], s[i | j], asc);
-            }
+    if (k_only == 0) {
+        smem_round_tail(s, n, g0, 2, min(256, n));  // stages 2..256 entirely in registers / shuffles
+        __syncthreads();
+        for (int64_t k = 512; k <= n; k <<= 1) {
+            smem_steps_down_to_256(s, n, g0, k, (int)(k >> 1));
+            smem_round_tail(s, n, g0, k, k);
             __syncthreads();
         }
+    } else {
+        smem_steps_down_to_256(s, n, g0, k_only, n >> 1);
+        smem_round_tail(s, n, g0, k_only, k_only);
+        __syncthreads();
     }
     for (int i = threadIdx.x; i < n; i += kSortThreads) base[i] = s[i];
 }
