@@ -56,7 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = os.environ.get("ARVAE_NVCC_EXTRA", "").split()  # experiments only (e.g. -DARVAE_TILE_THREADS=256)
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         p = subprocess.run(cmd, capture_output=True, text=True, env=env)
         log = p.stdout + p.stderr
         with open(obj + ".log", "w") as f:

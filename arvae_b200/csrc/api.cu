@@ -228,6 +228,14 @@ int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_
     return 0;
 }
 
+// experiments only (not in the public header): byte offset of the per-CTA timestamp buffer and CTA count
+extern "C" __attribute__((visibility("default"))) int64_t arvae_debug_times_offset(int64_t B_total, int64_t n_rows,
+                                                                                 int32_t R, int32_t *g_max_out) {
+    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count());
+    if (g_max_out) *g_max_out = LS.G_max;
+    return (int64_t)LS.off_dbg;
+}
+
 int arvae_reg_loss_scatter_bwd_f32(const float *grad_cols_dev, const float *grad_out_dev,
                                    const int32_t *reg_dims_host, int32_t R, int64_t n_rows,
                                    int64_t Z, float *grad_z_dev, int64_t gz_row_stride,

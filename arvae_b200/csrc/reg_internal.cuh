@@ -58,8 +58,8 @@ struct SortedLayout {
     int n_row_tiles, S;
     int64_t n_rr, F;
     int G_max, max_segs;
-    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_pgrad, off_prow,
-        off_lossp, bytes;
+    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_cls8, off_cost8, off_combo, off_prefix, off_pgrad, off_prow,
+        off_lossp, off_dbg, bytes;
 };
 int64_t sort_padded_size(int64_t B);
 int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, int64_t B,

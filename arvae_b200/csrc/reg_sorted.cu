@@ -4,7 +4,7 @@
 // reorganised so that almost every pair costs 1 MUFU + 4 FP32 instructions instead of 2 + 12:
 //
 //  * rows and columns of each regularised dim are ordered by attribute value (sort.cu).  A tile of
-//    512 rows x 256 columns whose attribute ranges do not overlap has a CONSTANT sign s_ij, so per
+//    128 rows (one warp) x 256 columns whose attribute ranges do not overlap has a CONSTANT sign s_ij, so per
 //    pair only sum(r) and sum(r^2) are needed, r = (1 - t)/2:
 //        s = +1:  |t - s| = 2r        g = -(1 - t^2) = -4 (r - r^2)
 //        s = -1:  |t - s| = 2(1 - r)  g = +4 (r - r^2)
@@ -24,17 +24,23 @@
 //  * work is split into fine units (row tile, 256-column sub-chunk) laid out linearly and divided
 //    EVENLY over a persistent grid (one contiguous range per CTA), so there is no wave tail; row
 //    partials go to a deterministic (segment, row tile) slot and are reduced in fixed order.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "reg_internal.cuh"
 
 namespace arvae {
 
-constexpr int kTileThreads = 128;
+#ifndef ARVAE_TILE_THREADS
+#define ARVAE_TILE_THREADS 256
+#endif
+constexpr int kTileThreads = ARVAE_TILE_THREADS;
 constexpr int kTileRI = 4;
-constexpr int kTileRows = kTileThreads * kTileRI;  // 512 rows per row tile
+constexpr int kTileRows = kTileThreads * kTileRI;  // 1024 rows per row tile (8 warps x 128 rows; 2 CTAs/SM: best measured)
 constexpr int kStageCols = 2048;                   // columns staged per __syncthreads pair
 constexpr float kMufu1MaxAbsU = 62.0f;
 static_assert(kTileRows / (kTileThreads / 32) == kTileRI * 32, "a warp owns kTileRI x 32 consecutive rows");
+static_assert(kTileThreads / 32 <= 16, "class word holds 16 warps");
 
 // ------------------------------------------------------------------------------------------------
 // gather the sorted order: Us/As/Es[r][k] for sorted position k, perm[r][k] = original index
@@ -275,11 +281,151 @@ struct TilesArgs {
     int G;                      // persistent CTAs
     int64_t n_rr;               // R * n_row_tiles
     int force_general;          // treat every tile as general (unsorted input / debugging)
+    // plan (plan_classes_kernel / plan_scan_kernel): per fine unit in VISITING order u = rr * S + s'
+    unsigned int *cls8;         // [F] 2-bit tile class per warp (bits 2w..2w+1, up to 16 warps)
+    unsigned short *cost8;      // [F] modelled cost of the unit (sum over the tile's warps)
+    long long *prefix;          // [n_rr + 1] exclusive prefix of the per-row-tile cost totals; [n_rr] = T
     double *pgrad, *prow, *lossp;
+    unsigned long long *dbg_times;  // [G][2] globaltimer at CTA start / end (experiments), or null
 };
 
-__host__ __device__ __forceinline__ int64_t cta_of_unit(int64_t f, int64_t F, int64_t G) {
-    return ((f + 1) * G + F - 1) / F - 1;  // largest c with floor(c F / G) <= f
+// Work split: unit u starts at cost position p(u) (exclusive prefix of the modelled costs in visiting
+// order); CTA c of G owns the units with floor(p G / T) == c, i.e. p in [ceil(cT/G), ceil((c+1)T/G)).
+__device__ __forceinline__ long long owner_of_pos(long long p, long long T, long long G) {
+    return (p * G) / T;
+}
+__device__ __forceinline__ long long ceil_share(long long c, long long T, long long G) {
+    return (c * T + G - 1) / G;
+}
+
+// modelled cost (issue/MUFU cycles per 32 pairs) of one warp's 128 x 256 tile, by class and tanh form
+__device__ __forceinline__ int class_cost(int cls, bool mufu1) {
+    // general, pos, neg, tie
+    return mufu1 ? ((0x0B08'0813u >> (8 * cls)) & 0xFF)   // 19, 8, 8, 11
+                 : ((0x1010'1014u >> (8 * cls)) & 0xFF);  // 20, 16, 16, 16
+}
+
+// One CTA per row tile rr: class byte and cost of each of its S units (in visiting order), and the
+// row tile's total cost.
+__global__ void __launch_bounds__(256)
+plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost) {
+    __shared__ float wmin[kTileThreads / 32], wmax[kTileThreads / 32];
+    __shared__ int whas[kTileThreads / 32];
+    __shared__ int sred[8];
+    const int64_t rr = blockIdx.x;
+    const int r = (int)(rr / a.n_row_tiles), I = (int)(rr % a.n_row_tiles);
+    const float *Ar = a.As + (int64_t)r * a.Bpad;
+    const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
+    const bool mufu1 = a.flags[r] == 0;
+    constexpr int kWarpRows = kTileRows / (kTileThreads / 32);
+    if (threadIdx.x < kTileThreads / 32) {
+        const int64_t m0 = (int64_t)I * kTileRows + (int64_t)threadIdx.x * kWarpRows;
+        const int64_t ml = min(m0 + kWarpRows, a.n_rows) - 1;
+        const bool has = m0 < a.n_rows;
+        whas[threadIdx.x] = has;
+        wmin[threadIdx.x] = has ? Ar[rp ? rp[m0] : m0] : 0.0f;
+        wmax[threadIdx.x] = has ? Ar[rp ? rp[ml] : ml] : 0.0f;
+    }
+    __syncthreads();
+    int total = 0;
+    for (int sp = threadIdx.x; sp < a.S; sp += 256) {
+        const int64_t col = (((int64_t)sp * a.P) % a.S) * kSubCols;
+        const float cmin = Ar[col], cmax = Ar[col + kSubCols - 1];
+        unsigned int cls8 = 0;
+        int cost = 0;
+#pragma unroll
+        for (int w = 0; w < kTileThreads / 32; ++w) {
+            const int cls = a.force_general ? (int)kClassGeneral : classify(wmin[w], wmax[w], cmin, cmax);
+            cls8 |= (unsigned int)cls << (2 * w);
+            if (whas[w]) cost += class_cost(cls, mufu1);
+        }
+        a.cls8[rr * a.S + sp] = cls8;
+        a.cost8[rr * a.S + sp] = (unsigned short)cost;
+        total += cost;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += sred[w];
+        combo_cost[rr] = t;
+    }
+}
+
+// prefix[rr] = sum of combo_cost[0..rr) ; prefix[n_rr] = T.   One CTA.
+__global__ void __launch_bounds__(1024)
+plan_scan_kernel(const int *__restrict__ combo_cost, int64_t n_rr, long long *__restrict__ prefix) {
+    __shared__ long long swarp[32];
+    __shared__ long long scarry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) scarry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_rr; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = i < n_rr ? (long long)combo_cost[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const long long w = swarp[lane];
+            long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            swarp[lane] = wi - w;
+        }
+        __syncthreads();
+        const long long excl = scarry + swarp[warp] + incl - v;
+        if (i < n_rr) prefix[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) scarry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n_rr] = scarry;
+}
+
+// First unit (rr, s') whose cost position is >= target; (n_rr, 0) when target >= T.  Cooperative over the CTA.
+__device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, int *s_out /*smem [2]*/,
+                                          int *s_scan /*smem [kTileThreads]*/) {
+    // largest rr with prefix[rr] <= target (every thread does the same search; prefix is tiny and cached)
+    long long lo = 0, hi = a.n_rr;  // prefix[0] = 0 <= target
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) >> 1;
+        if (a.prefix[mid] <= target) lo = mid; else hi = mid - 1;
+    }
+    if (lo >= a.n_rr) {
+        if (threadIdx.x == 0) { s_out[0] = (int)a.n_rr; s_out[1] = 0; }
+        __syncthreads();
+        return;
+    }
+    const long long need = target - a.prefix[lo];  // smallest s' with W(s') >= need, W = within-prefix
+    const unsigned short *cost = a.cost8 + lo * a.S;
+    const int per = (a.S + kTileThreads - 1) / kTileThreads;
+    const int q0 = min((int)threadIdx.x * per, a.S), q1 = min(q0 + per, a.S);
+    int mine = 0;
+    for (int q = q0; q < q1; ++q) mine += cost[q];
+    s_scan[threadIdx.x] = mine;
+    if (threadIdx.x == 0) { s_out[0] = (int)lo + 1; s_out[1] = 0; }  // default: past the end of this row tile
+    __syncthreads();
+    int before = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) before += s_scan[t];
+    // the crossing lies in exactly one thread's piece: W(q0) < need <= W(q1) or need <= W(q0) == 0 at q0 = 0
+    if (need <= before + mine && (need > before || threadIdx.x == 0) && q0 < q1) {
+        int w = before, q = q0;
+        while (q < q1 && w < need) w += cost[q++];
+        // q = first index with W(q) >= need, provided it is still inside this row tile
+        if (w >= need) { s_out[0] = (int)lo; s_out[1] = q; if (q >= a.S) { s_out[0] = (int)lo + 1; s_out[1] = 0; } }
+    }
+    __syncthreads();
 }
 
 template <bool MUFU1, bool GRAD>
@@ -300,15 +446,26 @@ reg_tiles_kernel(TilesArgs a) {
     __shared__ __align__(16) float sa[kStageCols];
     __shared__ double sred[kTileThreads / 32];
 
-    const int64_t c = blockIdx.x;
-    int64_t f = (c * a.F) / a.G;
-    const int64_t f_end = ((c + 1) * a.F) / a.G;
+    __shared__ int s_rng[4];
+    __shared__ int s_scan[kTileThreads];
+    const long long c = blockIdx.x;
+    if (a.dbg_times && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.dbg_times[2 * c] = t;
+    }
+    const long long T = a.prefix[a.n_rr];
+    find_unit(a, ceil_share(c, T, a.G), s_rng, s_scan);
+    find_unit(a, ceil_share(c + 1, T, a.G), s_rng + 2, s_scan);
+    int64_t rr = s_rng[0];
+    int sp0 = s_rng[1];
+    const int64_t rr_end = s_rng[2];
+    const int sp_end = s_rng[3];
     double lthread = 0.0;
 
-    while (f < f_end) {
-        const int64_t rr = f / a.S;
-        const int s0 = (int)(f % a.S);
-        const int s1 = (int)min((int64_t)a.S, (int64_t)s0 + (f_end - f));
+    while (rr < rr_end || (rr == rr_end && sp0 < sp_end)) {
+        const int s0 = sp0;
+        const int s1 = (rr == rr_end) ? sp_end : a.S;
         const int r = (int)(rr / a.n_row_tiles);
         const int I = (int)(rr % a.n_row_tiles);
         const bool mufu1 = a.flags[r] == 0;
@@ -324,7 +481,6 @@ reg_tiles_kernel(TilesArgs a) {
         const int64_t m0 = (int64_t)I * kTileRows + (int64_t)warp * (kTileRows / (kTileThreads / 32));
         const int64_t mlast = min(m0 + kTileRows / (kTileThreads / 32), a.n_rows) - 1;
         const bool warp_has_rows = m0 < a.n_rows;
-        const float amin = warp_has_rows ? Ar[rp ? rp[m0] : m0] : 0.0f;
         const float amax = warp_has_rows ? Ar[rp ? rp[mlast] : mlast] : 0.0f;
 
         RowRegs R;
@@ -358,16 +514,18 @@ reg_tiles_kernel(TilesArgs a) {
                 *reinterpret_cast<float4 *>(sa + q) = *reinterpret_cast<const float4 *>(Ar + col);
             }
             __syncthreads();
-            for (int sub = 0; sub < nsub * kSubCols; sub += kSubCols) {
-                const int cls = a.force_general ? (int)kClassGeneral
-                                                : classify(amin, amax, sa[sub], sa[sub + kSubCols - 1]);
-                if (mufu1) sweep_subchunk<true, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
-                else sweep_subchunk<false, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
+            if (warp_has_rows) {
+                for (int w = 0; w < nsub; ++w) {
+                    const int sub = w * kSubCols;
+                    const int cls = (a.cls8[rr * a.S + sp + w] >> (2 * warp)) & 3;  // planned class of this warp's tile
+                    if (mufu1) sweep_subchunk<true, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
+                    else sweep_subchunk<false, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
+                }
             }
         }
 
         // this CTA's segment of row tile rr: deterministic slot (segment index, rr)
-        const int64_t seg = c - cta_of_unit(rr * a.S, a.F, a.G);
+        const int64_t seg = c - owner_of_pos(a.prefix[rr], T, a.G);
         const int64_t slot = (seg * a.n_rr + rr) * kTileRows;
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
@@ -376,7 +534,8 @@ reg_tiles_kernel(TilesArgs a) {
             if (GRAD) a.pgrad[o] = dg[k];
             if (a.prow) a.prow[o] = dl[k];
         }
-        f += (s1 - s0);
+        ++rr;
+        sp0 = 0;
     }
 
     lthread = warp_sum(lthread);
@@ -387,6 +546,11 @@ reg_tiles_kernel(TilesArgs a) {
 #pragma unroll
         for (int w = 0; w < kTileThreads / 32; ++w) t += sred[w];
         a.lossp[c] = t;
+        if (a.dbg_times) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            a.dbg_times[2 * c + 1] = tt;
+        }
     }
 }
 
@@ -401,8 +565,9 @@ reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int6
         const int64_t m = idx % a.n_rows;
         const int64_t I = m / kTileRows, lr = m % kTileRows;
         const int64_t rr = (int64_t)r * a.n_row_tiles + I;
-        const int64_t c0 = cta_of_unit(rr * a.S, a.F, a.G);
-        const int64_t c1 = cta_of_unit(rr * a.S + a.S - 1, a.F, a.G);
+        const long long T = a.prefix[a.n_rr];
+        const int64_t c0 = owner_of_pos(a.prefix[rr], T, a.G);
+        const int64_t c1 = owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G);
         const int64_t pos = a.rowpos ? (int64_t)a.rowpos[(int64_t)r * a.n_rows + m] : m;
         const int64_t out = ((int64_t)perm[(int64_t)r * a.Bpad + pos] - row_begin) * R + r;
         if (grad_cols) {
@@ -476,9 +641,10 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count)
     // the larger occupancy of the two kernel variants bounds the slot count for both
     const int per_sm = 8;
     int64_t G = (int64_t)sm_count * per_sm;
-    if (G > L.F) G = L.F;
+    if (G > L.F / 4) G = L.F / 4;  // >= 4 units per CTA on average: every CTA owns at least one unit
     L.G_max = (int)(G > 0 ? G : 1);
-    L.max_segs = (int)(L.G_max / L.n_rr + 2);
+    // a row tile's share of the CTAs is at most (max unit cost / min unit cost) = 2.5 x the average
+    L.max_segs = (int)((5 * (int64_t)L.G_max + 2 * L.n_rr - 1) / (2 * L.n_rr) + 2);
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -493,9 +659,14 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count)
     L.off_rowpos = take(sizeof(int) * (size_t)R * (n_rows > 0 ? n_rows : 1));
     L.off_flags = take(sizeof(int) * ARVAE_MAX_REG_DIMS);
     L.off_blockcnt = take(sizeof(int) * (size_t)R * (size_t)ceil_div(L.Bpad, 256));
+    L.off_cls8 = take(sizeof(unsigned int) * (size_t)L.F);
+    L.off_cost8 = take(sizeof(unsigned short) * (size_t)L.F);
+    L.off_combo = take(sizeof(int) * (size_t)L.n_rr);
+    L.off_prefix = take(sizeof(long long) * (size_t)(L.n_rr + 1));
     L.off_pgrad = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
     L.off_prow = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
     L.off_lossp = take(sizeof(double) * (size_t)L.G_max);
+    L.off_dbg = take(sizeof(unsigned long long) * 2 * (size_t)L.G_max);
     L.bytes = off;
     return L;
 }
@@ -539,16 +710,26 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     a.Bpad = L.Bpad; a.n_rows = n_rows;
     a.n_row_tiles = L.n_row_tiles; a.S = L.S; a.F = L.F; a.n_rr = L.n_rr;
     a.P = golden_stride(L.S);
+    if (const char *dbg = getenv("ARVAE_DEBUG_STRIDE")) a.P = atoi(dbg) > 0 ? atoi(dbg) : a.P;  // experiments only
     int64_t G = (int64_t)sm_count() * tiles_ctas_per_sm(want_grad);
     if (G > L.G_max) G = L.G_max;
     if (G < 1) G = 1;
     a.G = (int)G;
     a.force_general = 0;
+    a.cls8 = reinterpret_cast<unsigned int *>(ws + L.off_cls8);
+    a.cost8 = reinterpret_cast<unsigned short *>(ws + L.off_cost8);
+    a.prefix = reinterpret_cast<long long *>(ws + L.off_prefix);
+    int *combo_cost = reinterpret_cast<int *>(ws + L.off_combo);
     a.pgrad = reinterpret_cast<double *>(ws + L.off_pgrad);
     a.prow = P.row_loss_out ? reinterpret_cast<double *>(ws + L.off_prow) : nullptr;
     a.lossp = reinterpret_cast<double *>(ws + L.off_lossp);
+    a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
 
     if (n_rows > 0) {
+        plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);
+        ARVAE_LAUNCH_CHECK("plan_classes_kernel");
+        plan_scan_kernel<<<1, 1024, 0, st>>>(combo_cost, L.n_rr, a.prefix);
+        ARVAE_LAUNCH_CHECK("plan_scan_kernel");
         profile_begin(st);
         if (want_grad) reg_tiles_kernel<true><<<a.G, kTileThreads, 0, st>>>(a);
         else reg_tiles_kernel<false><<<a.G, kTileThreads, 0, st>>>(a);
