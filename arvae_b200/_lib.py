@@ -13,7 +13,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libarvae_b200.so")
 
-ALGO_AUTO, ALGO_DENSE, ALGO_SORTED = 0, 1, 2
+ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, ALGO_TRIANGLE = 0, 1, 2, 3
 MAX_REG_DIMS = 32
 
 _c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -29,6 +29,7 @@ SIGNATURES = {
     "arvae_last_error": (ctypes.c_char_p, []),
     "arvae_device_sm_count": (ctypes.c_int, []),
     "arvae_reg_loss_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "arvae_reg_loss_workspace_bytes_algo": (_sz, [_i64, _i64, _i32, _i32]),
     "arvae_reg_loss_fwdbwd_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _c_i32p, _c_i32p, _i32,
                                                  _i64, _i64, _i64, _f, _f, _i32, _vp, _vp, _vp, _vp, _vp,
                                                  _sz, _vp]),

@@ -154,11 +154,15 @@ int arvae_device_sm_count(void) {
     return sm_count();
 }
 
-size_t arvae_reg_loss_workspace_bytes(int64_t B_total, int64_t n_rows, int32_t R) {
+size_t arvae_reg_loss_workspace_bytes_algo(int64_t B_total, int64_t n_rows, int32_t R, int32_t algo) {
     if (B_total < 0 || n_rows < 0 || R < 0 || R > ARVAE_MAX_REG_DIMS) return 0;
     const size_t d = dense_layout(B_total, n_rows, R > 0 ? R : 1, sm_count()).bytes;
-    const size_t s = sorted_layout(B_total, n_rows, R > 0 ? R : 1, sm_count()).bytes;
+    const size_t s = sorted_layout(B_total, n_rows, R > 0 ? R : 1, sm_count(), algo == ARVAE_ALGO_TRIANGLE).bytes;
     return d > s ? d : s;
+}
+
+size_t arvae_reg_loss_workspace_bytes(int64_t B_total, int64_t n_rows, int32_t R) {
+    return arvae_reg_loss_workspace_bytes_algo(B_total, n_rows, R, ARVAE_ALGO_AUTO);
 }
 
 int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t z_col_stride,
@@ -181,7 +185,7 @@ int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t 
         set_error("null pointer argument");
         return ARVAE_E_BADARG;
     }
-    if (algo != ARVAE_ALGO_AUTO && algo != ARVAE_ALGO_DENSE && algo != ARVAE_ALGO_SORTED) {
+    if (algo != ARVAE_ALGO_AUTO && algo != ARVAE_ALGO_DENSE && algo != ARVAE_ALGO_SORTED && algo != ARVAE_ALGO_TRIANGLE) {
         set_error("unknown algo %d", algo);
         return ARVAE_E_BADARG;
     }
@@ -192,9 +196,11 @@ int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t 
     P.loss_out = loss_out_dev; P.loss_f32_out = loss_f32_out_dev; P.grad_cols_out = grad_cols_out_dev; P.row_loss_out = row_loss_out_dev;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-    const bool sorted = algo == ARVAE_ALGO_SORTED || (algo == ARVAE_ALGO_AUTO && B_total >= kSortedMinBatch);
+    const bool sorted = algo == ARVAE_ALGO_SORTED || algo == ARVAE_ALGO_TRIANGLE ||
+                        (algo == ARVAE_ALGO_AUTO && B_total >= kSortedMinBatch);
+    P.use_triangle = algo == ARVAE_ALGO_TRIANGLE;
     const DenseLayout L = dense_layout(B_total, row_end - row_begin, R > 0 ? R : 1, sm_count());
-    const SortedLayout LS = sorted_layout(B_total, row_end - row_begin, R > 0 ? R : 1, sm_count());
+    const SortedLayout LS = sorted_layout(B_total, row_end - row_begin, R > 0 ? R : 1, sm_count(), P.use_triangle);
     const size_t need = sorted ? LS.bytes : L.bytes;
     if (workspace_bytes < need) {
         set_error("workspace too small: %zu < %zu", workspace_bytes, need);
@@ -215,12 +221,13 @@ int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_
         set_error("bad argument to path_flags");
         return ARVAE_E_BADARG;
     }
-    const bool sorted = algo == ARVAE_ALGO_SORTED || (algo == ARVAE_ALGO_AUTO && B_total >= kSortedMinBatch);
+    const bool sorted = algo == ARVAE_ALGO_SORTED || algo == ARVAE_ALGO_TRIANGLE ||
+                        (algo == ARVAE_ALGO_AUTO && B_total >= kSortedMinBatch);
     if (!sorted) {
         set_error("dense path selected for this shape: 2 MUFU per pair");
         return ARVAE_E_BADARG;
     }
-    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count());
+    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count(), algo == ARVAE_ALGO_TRIANGLE);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     ARVAE_CUDA_TRY(cudaMemcpyAsync(flags_out_host, reinterpret_cast<const char *>(workspace_dev) + LS.off_flags,
                                    sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st));
@@ -231,7 +238,7 @@ int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_
 // experiments only (not in the public header): byte offset of the per-CTA timestamp buffer and CTA count
 extern "C" __attribute__((visibility("default"))) int64_t arvae_debug_times_offset(int64_t B_total, int64_t n_rows,
                                                                                  int32_t R, int32_t *g_max_out) {
-    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count());
+    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count(), true);
     if (g_max_out) *g_max_out = LS.G_max;
     return (int64_t)LS.off_dbg;
 }
@@ -320,7 +327,7 @@ int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z, const flo
     const size_t zb = sizeof(float) * (size_t)(B > 0 ? B : 1) * Z;
     const size_t lb = sizeof(float) * (size_t)(B > 0 ? B : 1) * A;
     const size_t gb = sizeof(float) * (size_t)(B > 0 ? B : 1) * (R > 0 ? R : 1);
-    const size_t wb = arvae_reg_loss_workspace_bytes(B, B, R);
+    const size_t wb = arvae_reg_loss_workspace_bytes_algo(B, B, R, algo);
     if (C.z_bytes < zb) {
         cudaFree(C.z); cudaFree(C.gz);
         ARVAE_CUDA_TRY(cudaMalloc(&C.z, zb));

@@ -30,7 +30,7 @@ void profile_end(cudaStream_t st);
         if (_e != cudaSuccess) return ::arvae::fail_cuda(_e, name);   \
     } while (0)
 
-static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 // ---- device math ------------------------------------------------------------------------------

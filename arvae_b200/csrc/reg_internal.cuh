@@ -29,6 +29,7 @@ struct RegProblem {
     float *loss_f32_out;   // [1] or null
     float *grad_cols_out;  // [n_rows, R] or null
     double *row_loss_out;  // [n_rows, R] or null
+    bool use_triangle = false;  // sorted path, all rows: evaluate constant-sign tiles once for both sides
 };
 
 struct DenseLayout {
@@ -59,12 +60,12 @@ struct SortedLayout {
     int64_t n_rr, F;
     int G_max, max_segs;
     size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_cls8, off_cost8, off_combo, off_prefix, off_pgrad, off_prow,
-        off_lossp, off_dbg, bytes;
+        off_lossp, off_dbg, off_colpart, off_eloss, bytes;
 };
 int64_t sort_padded_size(int64_t B);
 int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, int64_t B,
                   int64_t N, unsigned long long *keys, cudaStream_t st);
-SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count);
+SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count, bool with_triangle = false);
 int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStream_t st);
 constexpr int64_t kSortedMinBatch = 8192;  // ARVAE_ALGO_AUTO switches to the sorted path from here
 

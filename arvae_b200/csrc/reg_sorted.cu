@@ -171,12 +171,13 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
 template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void loop_tie(const RowRegs &R, const float *__restrict__ se,
                                          const float *__restrict__ sx, float cabs,
-                                         double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+                                         double (&dl)[kTileRI], double (&dg)[kTileRI],
+                                         int ncols = kSubCols) {
     float lacc[kTileRI], gacc[kTileRI];
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = 0.0f;
 #pragma unroll 2
-    for (int q = 0; q < kSubCols; q += 4) {
+    for (int q = 0; q < ncols; q += 4) {
         const float4 xj = *reinterpret_cast<const float4 *>(sx + q);
         const float xx[4] = {xj.x, xj.y, xj.z, xj.w};
         float ee[4] = {0.f, 0.f, 0.f, 0.f};
@@ -211,12 +212,13 @@ template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void loop_general(const RowRegs &R, const float *__restrict__ se,
                                              const float *__restrict__ sx,
                                              const float *__restrict__ sa, float cabs,
-                                             double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+                                             double (&dl)[kTileRI], double (&dg)[kTileRI],
+                                             int ncols = kSubCols) {
     float lacc[kTileRI], gacc[kTileRI];
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = 0.0f;
 #pragma unroll 2
-    for (int q = 0; q < kSubCols; q += 4) {
+    for (int q = 0; q < ncols; q += 4) {
         const float4 xj = *reinterpret_cast<const float4 *>(sx + q);
         const float4 aj = *reinterpret_cast<const float4 *>(sa + q);
         const float xx[4] = {xj.x, xj.y, xj.z, xj.w};
@@ -287,6 +289,11 @@ struct TilesArgs {
     long long *prefix;          // [n_rr + 1] exclusive prefix of the per-row-tile cost totals; [n_rr] = T
     double *pgrad, *prow, *lossp;
     unsigned long long *dbg_times;  // [G][2] globaltimer at CTA start / end (experiments), or null
+    // triangle mode (reg_tri.cuh)
+    float2 *colpart;            // per (row tile, column at or above it): column sums (sum r, sum r^2) of double-duty tiles
+    int Pinv;                   // inverse of P modulo S
+    int64_t B;                  // number of real columns (= rows in triangle mode)
+    int max_segs;               // segment slots per row tile
 };
 
 // Work split: unit u starts at cost position p(u) (exclusive prefix of the modelled costs in visiting
@@ -393,37 +400,54 @@ plan_scan_kernel(const int *__restrict__ combo_cost, int64_t n_rr, long long *__
     if (threadIdx.x == 0) prefix[n_rr] = scarry;
 }
 
-// First unit (rr, s') whose cost position is >= target; (n_rr, 0) when target >= T.  Cooperative over the CTA.
+// First unit (rr, s') whose cost position is >= target; (n_rr, 0) when target >= T.  Cooperative over the
+// CTA (kTileThreads threads): one parallel pass over the row-tile prefix, one block scan over the row tile's
+// unit costs.
 __device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, int *s_out /*smem [2]*/,
                                           int *s_scan /*smem [kTileThreads]*/) {
-    // largest rr with prefix[rr] <= target (every thread does the same search; prefix is tiny and cached)
-    long long lo = 0, hi = a.n_rr;  // prefix[0] = 0 <= target
-    while (lo < hi) {
-        const long long mid = (lo + hi + 1) >> 1;
-        if (a.prefix[mid] <= target) lo = mid; else hi = mid - 1;
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // lo = (number of rr in [0, n_rr] with prefix[rr] <= target) - 1   (prefix is non-decreasing, prefix[0] = 0)
+    int cnt = 0;
+    for (long long i = threadIdx.x; i <= a.n_rr; i += kTileThreads) cnt += a.prefix[i] <= target;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_scan[warp] = cnt;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < kTileThreads / 32; ++w) tot += s_scan[w];
+    const long long lo = (long long)tot - 1;
+    __syncthreads();
     if (lo >= a.n_rr) {
         if (threadIdx.x == 0) { s_out[0] = (int)a.n_rr; s_out[1] = 0; }
         __syncthreads();
         return;
     }
-    const long long need = target - a.prefix[lo];  // smallest s' with W(s') >= need, W = within-prefix
+    const long long need = target - a.prefix[lo];  // smallest s' with W(s') >= need, W = exclusive within-tile prefix
     const unsigned short *cost = a.cost8 + lo * a.S;
     const int per = (a.S + kTileThreads - 1) / kTileThreads;
     const int q0 = min((int)threadIdx.x * per, a.S), q1 = min(q0 + per, a.S);
     int mine = 0;
     for (int q = q0; q < q1; ++q) mine += cost[q];
-    s_scan[threadIdx.x] = mine;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_scan[warp] = incl;
     if (threadIdx.x == 0) { s_out[0] = (int)lo + 1; s_out[1] = 0; }  // default: past the end of this row tile
     __syncthreads();
-    int before = 0;
-    for (int t = 0; t < (int)threadIdx.x; ++t) before += s_scan[t];
-    // the crossing lies in exactly one thread's piece: W(q0) < need <= W(q1) or need <= W(q0) == 0 at q0 = 0
+    int before = incl - mine;
+    for (int w = 0; w < warp; ++w) before += s_scan[w];
+    // the crossing lies in exactly one thread's piece: W(q0) < need <= W(q1), or need <= 0 at q0 = 0
     if (need <= before + mine && (need > before || threadIdx.x == 0) && q0 < q1) {
         int w = before, q = q0;
         while (q < q1 && w < need) w += cost[q++];
-        // q = first index with W(q) >= need, provided it is still inside this row tile
-        if (w >= need) { s_out[0] = (int)lo; s_out[1] = q; if (q >= a.S) { s_out[0] = (int)lo + 1; s_out[1] = 0; } }
+        if (w >= need) {
+            s_out[0] = (int)lo;
+            s_out[1] = q;
+            if (q >= a.S) { s_out[0] = (int)lo + 1; s_out[1] = 0; }
+        }
     }
     __syncthreads();
 }
@@ -630,7 +654,9 @@ static int tiles_ctas_per_sm(bool grad) {
     return v;
 }
 
-SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count) {
+#include "reg_tri.cuh"
+
+SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count, bool with_triangle) {
     SortedLayout L;
     L.N = sort_padded_size(B_total > 0 ? B_total : 1);
     L.Bpad = round_up(B_total > 0 ? B_total : 1, kSubCols);
@@ -645,6 +671,11 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count)
     L.G_max = (int)(G > 0 ? G : 1);
     // a row tile's share of the CTAs is at most (max unit cost / min unit cost) = 2.5 x the average
     L.max_segs = (int)((5 * (int64_t)L.G_max + 2 * L.n_rr - 1) / (2 * L.n_rr) + 2);
+    const bool tri_capable = with_triangle && (n_rows == B_total && B_total > 0);
+    if (tri_capable) {  // triangle mode: per-row-tile costs vary more (the first row tile has ~2x the average)
+        const int tri_segs = (int)((4 * (int64_t)L.G_max + L.n_rr - 1) / L.n_rr + 3);
+        if (tri_segs > L.max_segs) L.max_segs = tri_segs;
+    }
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -666,6 +697,8 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count)
     L.off_pgrad = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
     L.off_prow = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
     L.off_lossp = take(sizeof(double) * (size_t)L.G_max);
+    L.off_colpart = take(tri_capable ? sizeof(float2) * (size_t)R * (size_t)colpart_size(L.n_row_tiles, L.Bpad) : 0);
+    L.off_eloss = take(sizeof(double) * (size_t)(ceil_div((n_rows > 0 ? n_rows : 1) * (int64_t)R, 256)));
     L.off_dbg = take(sizeof(unsigned long long) * 2 * (size_t)L.G_max);
     L.bytes = off;
     return L;
@@ -724,6 +757,9 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     a.prow = P.row_loss_out ? reinterpret_cast<double *>(ws + L.off_prow) : nullptr;
     a.lossp = reinterpret_cast<double *>(ws + L.off_lossp);
     a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
+
+    a.colpart = nullptr; a.Pinv = 0; a.B = P.B; a.max_segs = L.max_segs;
+    if (P.use_triangle && all_rows && n_rows > 0) return run_reg_tri_tail(P, L, a, perm, combo_cost, ws, st);
 
     if (n_rows > 0) {
         plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);

@@ -28,8 +28,9 @@ import torch
 
 from . import _lib
 
-ALGO_AUTO, ALGO_DENSE, ALGO_SORTED = _lib.ALGO_AUTO, _lib.ALGO_DENSE, _lib.ALGO_SORTED
+ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, ALGO_TRIANGLE = _lib.ALGO_AUTO, _lib.ALGO_DENSE, _lib.ALGO_SORTED, _lib.ALGO_TRIANGLE
 HAVE_SORTED = True
+HAVE_TRIANGLE = True
 
 _EXACT_IN_F32 = (torch.float32, torch.float16, torch.bfloat16, torch.int8, torch.uint8, torch.int16,
                  torch.bool)
@@ -117,7 +118,7 @@ def _launch_reg(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], 
         loss32 = torch.empty((), dtype=torch.float32, device=dev)
         grad_cols = torch.empty((n_rows, R), dtype=torch.float32, device=dev) if want_grad else None
         row_loss = torch.empty((n_rows, R), dtype=torch.float64, device=dev) if want_row_loss else None
-        ws_bytes = int(lib.arvae_reg_loss_workspace_bytes(B, n_rows, R))
+        ws_bytes = int(lib.arvae_reg_loss_workspace_bytes_algo(B, n_rows, R, algo))
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         rc = lib.arvae_reg_loss_fwdbwd_f32(
             _ptr(z), z.stride(0), z.stride(1), _ptr(labels), labels.stride(0), labels.stride(1),
@@ -248,7 +249,7 @@ def mufu_per_pair(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int]
     B, R = z.shape[0], len(dims)
     with torch.cuda.device(z.device):
         loss64 = torch.empty((), dtype=torch.float64, device=z.device)
-        ws = torch.empty(max(int(lib.arvae_reg_loss_workspace_bytes(B, B, R)), 256), dtype=torch.uint8, device=z.device)
+        ws = torch.empty(max(int(lib.arvae_reg_loss_workspace_bytes_algo(B, B, R, int(algo))), 256), dtype=torch.uint8, device=z.device)
         rc = lib.arvae_reg_loss_fwdbwd_f32(_ptr(z), z.stride(0), z.stride(1), _ptr(lab), lab.stride(0), lab.stride(1),
                                            _lib.i32_array(dims), _lib.i32_array(lcols), R, 0, B, B, _scalar(gamma),
                                            _scalar(factor), int(algo), _ptr(loss64), None, None, None, _ptr(ws),

@@ -168,14 +168,33 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to stdout) write to
+    fd 1, so fd 1 is pointed at stderr for the whole run and the JSON goes to a private copy of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -383,7 +402,7 @@ def main():
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "loss": loss_val, "loss_e2e": loss_e2e,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -20,12 +20,15 @@ constexpr int ILP = 8;
 constexpr int ITERS = 4096;
 
 template <int KIND> __global__ void rate_kernel(float *out, float seed, unsigned long long *clk);
-enum Kind { K_EX2, K_RCP, K_TANH, K_FFMA, K_FADD, K_FMNMX, K_FSET, K_PAIR_CONST, K_PAIR_CONST1, K_PAIR_GENERAL, K_EX2_RCP, K_COUNT };
+enum Kind { K_EX2, K_RCP, K_TANH, K_FFMA, K_FADD, K_FMNMX, K_FSET, K_PAIR_CONST, K_PAIR_CONST1, K_PAIR_GENERAL, K_EX2_RCP, K_REDUX, K_SHFL, K_F2I, K_ATOMS, K_COUNT };
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 template <int KIND>
 __global__ void __launch_bounds__(256) rate_kernel(float *out, float seed, unsigned long long *clk) {
+    __shared__ unsigned int sm[64];
+    if (threadIdx.x < 64) sm[threadIdx.x] = 0;
+    __syncthreads();
     const long long c0 = clock64();
     const unsigned long long t0 = gtimer();
     float v[ILP], w[ILP];
@@ -44,6 +47,10 @@ __global__ void __launch_bounds__(256) rate_kernel(float *out, float seed, unsig
             if (KIND == K_FMNMX) v[k] = fminf(v[k], w[k] + 0.f), w[k] = fmaxf(w[k], c1);  // 2 FMNMX (w chain) -- counted as 2
             if (KIND == K_FSET) v[k] = (v[k] > c1 ? 1.0f : 0.0f) + 0.f, w[k] = (w[k] < c2 ? 1.0f : 0.0f);
             if (KIND == K_EX2_RCP) v[k] = rcpa(ex2a(v[k]));
+            if (KIND == K_REDUX) v[k] = __uint_as_float(__reduce_add_sync(0xffffffffu, __float_as_uint(v[k])) | 0x3f000000u);
+            if (KIND == K_SHFL) v[k] = __shfl_xor_sync(0xffffffffu, v[k], 1) + c1;
+            if (KIND == K_F2I) v[k] = (float)__float2uint_rn(v[k]) * c1;
+            if (KIND == K_ATOMS) atomicAdd(&sm[(threadIdx.x & 7) + 8 * k], (unsigned)it);
             if (KIND == K_PAIR_CONST) {      // constant-sign tile loop: FADD, EX2, FADD, RCP, FADD, FFMA
                 const float r = rcpa(ex2a(c1 - v[k]) + 1.0f);
                 v[k] += r;
@@ -70,7 +77,7 @@ __global__ void __launch_bounds__(256) rate_kernel(float *out, float seed, unsig
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < ILP; ++k) s += v[k] + w[k];
-    if (s == 123.456f) out[0] = s;
+    if (s == 123.456f) out[0] = s + sm[threadIdx.x & 63];
     if (blockIdx.x == 0 && threadIdx.x == 0) { clk[0] = (unsigned long long)(clock64() - c0); clk[1] = gtimer() - t0; }
 }
 
@@ -130,6 +137,10 @@ int main(int argc, char **argv) {
             run<K_PAIR_CONST>("pair_const_2mufu_4fp32", 1, sms, clk_ghz, out, w),
             run<K_PAIR_CONST1>("pair_const_1mufu_4fp32", 1, sms, clk_ghz, out, w),
             run<K_PAIR_GENERAL>("pair_general_2mufu_12", 1, sms, clk_ghz, out, w),
+            run<K_REDUX>("redux_sum_u32(+lop)", 1, sms, clk_ghz, out, w),
+            run<K_SHFL>("shfl_xor(+fadd)", 1, sms, clk_ghz, out, w),
+            run<K_F2I>("f2i+i2f+fmul", 1, sms, clk_ghz, out, w),
+            run<K_ATOMS>("atoms_add_8lanes_distinct", 1, sms, clk_ghz, out, w),
         };
         for (auto &r : rs) {
             printf("%s\"%s@%dw\": {\"per_clk_sm\": %.3f, \"ms\": %.4f, \"sm_ghz\": %.4f}", first ? "" : ", ", r.name, w, r.lanes_per_clk_sm, r.ms, r.ghz);

@@ -60,6 +60,7 @@ extern "C" {
 #define ARVAE_ALGO_AUTO 0
 #define ARVAE_ALGO_DENSE 1  /* every tile through the general pair loop (float compares)      */
 #define ARVAE_ALGO_SORTED 2 /* rows/columns ordered by attribute, constant-sign tile fast path */
+#define ARVAE_ALGO_TRIANGLE 3 /* sorted + each constant-sign tile evaluated once for both sides (all rows only) */
 
 ARVAE_API int arvae_version(void);
 ARVAE_API const char *arvae_last_error(void);
@@ -69,6 +70,8 @@ ARVAE_API int arvae_device_sm_count(void);
 
 /* Bytes of scratch the fused forward+backward needs for this shape. */
 ARVAE_API size_t arvae_reg_loss_workspace_bytes(int64_t B_total, int64_t n_rows, int32_t R);
+/* Same for an explicit algorithm (ARVAE_ALGO_TRIANGLE needs ~B^2 R / 128 bytes more for its column sums). */
+ARVAE_API size_t arvae_reg_loss_workspace_bytes_algo(int64_t B_total, int64_t n_rows, int32_t R, int32_t algo);
 
 /*
  * Fused forward + backward of  sum_r gamma * mean_ij | tanh(factor*(z[i,d_r]-z[j,d_r])) - sign(a[i,c_r]-a[j,c_r]) |

@@ -22,6 +22,8 @@ try:
     from arvae_b200 import ops as _ops
     if getattr(_ops, "HAVE_SORTED", False):
         ALGOS.append(2)
+    if getattr(_ops, "HAVE_TRIANGLE", False):
+        ALGOS.append(3)
 except Exception:  # pragma: no cover
     pass
 
