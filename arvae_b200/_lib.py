@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libarvae_b200.so")
+LIB_PATH = os.environ.get("ARVAE_LIB_PATH") or os.path.join(_HERE, "csrc", "libarvae_b200.so")  # override: A/B experiments
 
 ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, ALGO_TRIANGLE = 0, 1, 2, 3
 MAX_REG_DIMS = 32

@@ -237,8 +237,9 @@ int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_
 
 // experiments only (not in the public header): byte offset of the per-CTA timestamp buffer and CTA count
 extern "C" __attribute__((visibility("default"))) int64_t arvae_debug_times_offset(int64_t B_total, int64_t n_rows,
-                                                                                 int32_t R, int32_t *g_max_out) {
-    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count(), true);
+                                                                                 int32_t R, int32_t algo,
+                                                                                 int32_t *g_max_out) {
+    const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count(), algo == ARVAE_ALGO_TRIANGLE);
     if (g_max_out) *g_max_out = LS.G_max;
     return (int64_t)LS.off_dbg;
 }

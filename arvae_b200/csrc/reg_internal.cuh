@@ -59,6 +59,7 @@ struct SortedLayout {
     int n_row_tiles, S;
     int64_t n_rr, F;
     int G_max, max_segs;
+    size_t slot_bytes;
     size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_cls8, off_cost8, off_combo, off_prefix, off_pgrad, off_prow,
         off_lossp, off_dbg, off_colpart, off_eloss, bytes;
 };

@@ -120,6 +120,19 @@ row_select_kernel(const int *__restrict__ perm, const int *__restrict__ blockcnt
 // ------------------------------------------------------------------------------------------------
 // pair loops over one 256-column sub-chunk staged in shared memory
 // ------------------------------------------------------------------------------------------------
+// Row partial sums are carried in 2^-30 fixed point (int64): integer addition is associative, so a row's
+// total does not depend on how its column units were split between CTAs / CTA halves at run time (the split
+// is dynamic), and results stay bitwise reproducible.  |v| < 2^21 per call (a sub-chunk partial is <= 512).
+typedef long long acc_t;
+constexpr double kFixMagic = 6291456.0;              // 1.5 * 2^22: (v + magic) keeps round(v 2^30) in the mantissa
+constexpr double kFixScale = 1.0 / 1073741824.0;     // 2^-30
+// per-CTA loss partials drop 6 bits (2^-24): 6 B^2 R / #CTAs stays far below 2^63 up to B ~ 10^6
+constexpr int kLossShift = 6;
+constexpr double kLossScale = 1.0 / 16777216.0;      // 2^-24
+__device__ __forceinline__ void acc_add(acc_t &acc, float v) {
+    acc += __double_as_longlong((double)v + kFixMagic) - __double_as_longlong(kFixMagic);
+}
+
 // Per-thread row operands of one row tile.
 struct RowRegs {
     float e[kTileRI];  // 2^u_i          (1-MUFU form)
@@ -136,7 +149,7 @@ __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs)
 template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,
                                            const float *__restrict__ sx, float cabs, bool positive,
-                                           double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+                                           acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
     float A1[kTileRI][4], A2[kTileRI][4];
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k)
@@ -163,16 +176,15 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
         const float S1 = (A1[k][0] + A1[k][1]) + (A1[k][2] + A1[k][3]);
         const float S2 = (A2[k][0] + A2[k][1]) + (A2[k][2] + A2[k][3]);
         // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2)
-        dl[k] += (double)(positive ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
-        if (GRAD) dg[k] += (double)(positive ? S2 - S1 : S1 - S2);
+        acc_add(dl[k], positive ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
+        if (GRAD) acc_add(dg[k], positive ? S2 - S1 : S1 - S2);
     }
 }
 
-template <bool MUFU1, bool GRAD>
+template <bool MUFU1, bool GRAD, int ncols = kSubCols>
 __device__ __forceinline__ void loop_tie(const RowRegs &R, const float *__restrict__ se,
                                          const float *__restrict__ sx, float cabs,
-                                         double (&dl)[kTileRI], double (&dg)[kTileRI],
-                                         int ncols = kSubCols) {
+                                         acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
     float lacc[kTileRI], gacc[kTileRI];
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = 0.0f;
@@ -203,17 +215,16 @@ __device__ __forceinline__ void loop_tie(const RowRegs &R, const float *__restri
     }
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k) {
-        dl[k] += (double)(2.0f * lacc[k]);
-        if (GRAD) dg[k] += (double)gacc[k];
+        acc_add(dl[k], 2.0f * lacc[k]);
+        if (GRAD) acc_add(dg[k], gacc[k]);
     }
 }
 
-template <bool MUFU1, bool GRAD>
+template <bool MUFU1, bool GRAD, int ncols = kSubCols>
 __device__ __forceinline__ void loop_general(const RowRegs &R, const float *__restrict__ se,
                                              const float *__restrict__ sx,
                                              const float *__restrict__ sa, float cabs,
-                                             double (&dl)[kTileRI], double (&dg)[kTileRI],
-                                             int ncols = kSubCols) {
+                                             acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
     float lacc[kTileRI], gacc[kTileRI];
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = 0.0f;
@@ -251,8 +262,8 @@ __device__ __forceinline__ void loop_general(const RowRegs &R, const float *__re
     }
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k) {
-        dl[k] += (double)lacc[k];
-        if (GRAD) dg[k] += (double)gacc[k];
+        acc_add(dl[k], lacc[k]);
+        if (GRAD) acc_add(dg[k], gacc[k]);
     }
 }
 
@@ -287,7 +298,7 @@ struct TilesArgs {
     unsigned int *cls8;         // [F] 2-bit tile class per warp (bits 2w..2w+1, up to 16 warps)
     unsigned short *cost8;      // [F] modelled cost of the unit (sum over the tile's warps)
     long long *prefix;          // [n_rr + 1] exclusive prefix of the per-row-tile cost totals; [n_rr] = T
-    double *pgrad, *prow, *lossp;
+    acc_t *pgrad, *prow, *lossp;  // fixed-point row partials per slot; per-CTA loss partials
     unsigned long long *dbg_times;  // [G][2] globaltimer at CTA start / end (experiments), or null
     // triangle mode (reg_tri.cuh)
     float2 *colpart;            // per (row tile, column at or above it): column sums (sum r, sum r^2) of double-duty tiles
@@ -403,18 +414,19 @@ plan_scan_kernel(const int *__restrict__ combo_cost, int64_t n_rr, long long *__
 // First unit (rr, s') whose cost position is >= target; (n_rr, 0) when target >= T.  Cooperative over the
 // CTA (kTileThreads threads): one parallel pass over the row-tile prefix, one block scan over the row tile's
 // unit costs.
+template <int NT>
 __device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, int *s_out /*smem [2]*/,
-                                          int *s_scan /*smem [kTileThreads]*/) {
+                                          int *s_scan /*smem [NT]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // lo = (number of rr in [0, n_rr] with prefix[rr] <= target) - 1   (prefix is non-decreasing, prefix[0] = 0)
     int cnt = 0;
-    for (long long i = threadIdx.x; i <= a.n_rr; i += kTileThreads) cnt += a.prefix[i] <= target;
+    for (long long i = threadIdx.x; i <= a.n_rr; i += NT) cnt += a.prefix[i] <= target;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) s_scan[warp] = cnt;
     __syncthreads();
     int tot = 0;
-    for (int w = 0; w < kTileThreads / 32; ++w) tot += s_scan[w];
+    for (int w = 0; w < NT / 32; ++w) tot += s_scan[w];
     const long long lo = (long long)tot - 1;
     __syncthreads();
     if (lo >= a.n_rr) {
@@ -424,7 +436,7 @@ __device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, 
     }
     const long long need = target - a.prefix[lo];  // smallest s' with W(s') >= need, W = exclusive within-tile prefix
     const unsigned short *cost = a.cost8 + lo * a.S;
-    const int per = (a.S + kTileThreads - 1) / kTileThreads;
+    const int per = (a.S + NT - 1) / NT;
     const int q0 = min((int)threadIdx.x * per, a.S), q1 = min(q0 + per, a.S);
     int mine = 0;
     for (int q = q0; q < q1; ++q) mine += cost[q];
@@ -455,120 +467,170 @@ __device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, 
 template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const float *se,
                                                const float *sx, const float *sa, float cabs,
-                                               double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+                                               acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
     if (cls == kClassPos) loop_const<MUFU1, GRAD>(R, se, sx, cabs, true, dl, dg);
     else if (cls == kClassNeg) loop_const<MUFU1, GRAD>(R, se, sx, cabs, false, dl, dg);
     else if (cls == kClassTie) loop_tie<MUFU1, GRAD>(R, se, sx, cabs, dl, dg);
     else loop_general<MUFU1, GRAD>(R, se, sx, sa, cabs, dl, dg);
 }
 
-template <bool GRAD>
-__global__ void __launch_bounds__(kTileThreads)
-reg_tiles_kernel(TilesArgs a) {
-    __shared__ __align__(16) float se[kStageCols];
-    __shared__ __align__(16) float sx[kStageCols];
-    __shared__ __align__(16) float sa[kStageCols];
-    __shared__ double sred[kTileThreads / 32];
+// The pair kernel.  One CTA of 512 threads per SM, split into two independent halves of 8 warps (256 threads,
+// a 1024-row tile each, own staging buffers, own named barrier).  The CTA owns a contiguous, cost-balanced
+// range of units; the halves consume it from both ends -- the front half forward, the back half backward --
+// claiming a few units at a time from a shared counter until they meet.  Whichever half the SM's warp
+// arbitration favours simply takes more units, so both stay busy to the end (with two independent CTAs per
+// SM and a static split the favoured CTA finished at ~55 % of the kernel and the other ran alone, at lower
+// MUFU utilisation, for the rest).  Row partials are fixed-point integers, so the result does not depend on
+// where the halves meet.
+constexpr int kDuoThreads = 2 * kTileThreads;
+constexpr int kStageSubs = kStageCols / kSubCols;
+constexpr int kDuoStageBytes = 2 * 3 * kStageCols * (int)sizeof(float);  // 48 KiB
 
+__device__ __forceinline__ void half_barrier(int half) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(kTileThreads) : "memory");
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(kDuoThreads, 1)
+reg_tiles_kernel(TilesArgs a) {
+    extern __shared__ __align__(16) float stage[];  // [2 halves][3 arrays][kStageCols] = kDuoStageBytes (dynamic)
+    __shared__ acc_t sred[kDuoThreads / 32];
     __shared__ int s_rng[4];
-    __shared__ int s_scan[kTileThreads];
+    __shared__ int s_scan[kDuoThreads];
+    __shared__ unsigned int s_claimed;   // units granted so far (may overshoot N)
+    __shared__ int s_grant[2][2];        // per half: first unit (linear) and count of the current grant
+
     const long long c = blockIdx.x;
     if (a.dbg_times && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         a.dbg_times[2 * c] = t;
     }
+    if (threadIdx.x == 0) s_claimed = 0u;
     const long long T = a.prefix[a.n_rr];
-    find_unit(a, ceil_share(c, T, a.G), s_rng, s_scan);
-    find_unit(a, ceil_share(c + 1, T, a.G), s_rng + 2, s_scan);
-    int64_t rr = s_rng[0];
-    int sp0 = s_rng[1];
-    const int64_t rr_end = s_rng[2];
-    const int sp_end = s_rng[3];
-    double lthread = 0.0;
+    find_unit<kDuoThreads>(a, ceil_share(c, T, a.G), s_rng, s_scan);
+    find_unit<kDuoThreads>(a, ceil_share(c + 1, T, a.G), s_rng + 2, s_scan);
+    const int64_t rr0 = s_rng[0];
+    const int sp0 = s_rng[1];
+    const int64_t N = ((int64_t)s_rng[2] - rr0) * a.S + s_rng[3] - sp0;  // units of this CTA, linear index u:
+                                                                          // (rr, s') = (rr0 + (sp0+u)/S, (sp0+u)%S)
+    const int half = threadIdx.x / kTileThreads;
+    const int tid = threadIdx.x % kTileThreads;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarpRows = kTileRows / (kTileThreads / 32);
+    float *hse = stage + (half * 3 + 0) * kStageCols, *hsx = stage + (half * 3 + 1) * kStageCols,
+          *hsa = stage + (half * 3 + 2) * kStageCols;
 
-    while (rr < rr_end || (rr == rr_end && sp0 < sp_end)) {
-        const int s0 = sp0;
-        const int s1 = (rr == rr_end) ? sp_end : a.S;
-        const int r = (int)(rr / a.n_row_tiles);
-        const int I = (int)(rr % a.n_row_tiles);
-        const bool mufu1 = a.flags[r] == 0;
-        const float *Er = a.Es + (int64_t)r * a.Bpad;
-        const float *Xr = a.Xs + (int64_t)r * a.Bpad;
-        const float *Ar = a.As + (int64_t)r * a.Bpad;
-        const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
+    int64_t cursor = half == 0 ? 0 : N;  // next unit from the front / one past the next unit from the back
+    int64_t cur_rr = -1;
+    acc_t lthread = 0;
+    RowRegs R;
+    bool valid[kTileRI];
+    acc_t dl[kTileRI], dg[kTileRI];
+    bool warp_has_rows = false, mufu1 = true;
+    const float *Er = nullptr, *Xr = nullptr, *Ar = nullptr;
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k) { valid[k] = false; dl[k] = 0; dg[k] = 0; R.e[k] = 1.0f; R.x[k] = 0.0f; R.a[k] = 0.0f; }
 
-        // Each warp owns 128 CONSECUTIVE sorted rows of the tile (lane l, k -> row 128 w + 32 k + l) and
-        // classifies sub-chunks against ITS OWN attribute range: the general band a warp sees is as wide
-        // as 128 rows, not 512 (matters most for row-block shards, whose rows are 1/G of the columns).
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int64_t m0 = (int64_t)I * kTileRows + (int64_t)warp * (kTileRows / (kTileThreads / 32));
-        const int64_t mlast = min(m0 + kTileRows / (kTileThreads / 32), a.n_rows) - 1;
-        const bool warp_has_rows = m0 < a.n_rows;
-        const float amax = warp_has_rows ? Ar[rp ? rp[mlast] : mlast] : 0.0f;
-
-        RowRegs R;
-        bool valid[kTileRI];
-        double dl[kTileRI], dg[kTileRI];
+    // flush this half's partial sums of row tile cur_rr into its slot (segment of this CTA, half)
+    auto flush = [&]() {
+        if (cur_rr < 0) return;
+        const int64_t seg = c - owner_of_pos(a.prefix[cur_rr], T, a.G);
+        const int64_t slot = (((seg * 2 + half) * a.n_rr) + cur_rr) * kTileRows;
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
-            const int64_t m = m0 + (int64_t)k * 32 + lane;
-            valid[k] = m < a.n_rows;
-            const int64_t pos = valid[k] ? (rp ? (int64_t)rp[m] : m) : 0;
-            R.e[k] = valid[k] ? Er[pos] : 1.0f;
-            R.x[k] = valid[k] ? Xr[pos] : 0.0f;
-            R.a[k] = valid[k] ? Ar[pos] : amax;
-            dl[k] = 0.0;
-            dg[k] = 0.0;
-        }
-
-        // Sub-chunks are visited in a permuted order, s = (s' * P) mod S with P ~ 0.618 S coprime to S:
-        // any contiguous range of s' is spread evenly over the columns, so every CTA sees the same mix of
-        // cheap constant-sign tiles and expensive general / tie tiles (the general band of a row tile is
-        // contiguous in s and would otherwise land on a few CTAs).
-        constexpr int kStageSubs = kStageCols / kSubCols;
-        for (int sp = s0; sp < s1; sp += kStageSubs) {
-            const int nsub = min(kStageSubs, s1 - sp);
-            __syncthreads();
-            for (int q = threadIdx.x * 4; q < nsub * kSubCols; q += kTileThreads * 4) {
-                const int w = q / kSubCols;
-                const int64_t col = (((int64_t)(sp + w) * a.P) % a.S) * kSubCols + (q - w * kSubCols);
-                *reinterpret_cast<float4 *>(se + q) = *reinterpret_cast<const float4 *>(Er + col);
-                *reinterpret_cast<float4 *>(sx + q) = *reinterpret_cast<const float4 *>(Xr + col);
-                *reinterpret_cast<float4 *>(sa + q) = *reinterpret_cast<const float4 *>(Ar + col);
+            const int64_t o = slot + warp * kWarpRows + k * 32 + lane;  // = row - tile start
+            if (valid[k]) {
+                lthread += dl[k] >> kLossShift;
+                if (GRAD) a.pgrad[o] = dg[k];
+                if (a.prow) a.prow[o] = dl[k];
             }
-            __syncthreads();
-            if (warp_has_rows) {
-                for (int w = 0; w < nsub; ++w) {
-                    const int sub = w * kSubCols;
-                    const int cls = (a.cls8[rr * a.S + sp + w] >> (2 * warp)) & 3;  // planned class of this warp's tile
-                    if (mufu1) sweep_subchunk<true, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
-                    else sweep_subchunk<false, GRAD>(cls, R, se + sub, sx + sub, sa + sub, a.cabs, dl, dg);
-                }
-            }
+            dl[k] = 0;
+            dg[k] = 0;
         }
+    };
 
-        // this CTA's segment of row tile rr: deterministic slot (segment index, rr)
-        const int64_t seg = c - owner_of_pos(a.prefix[rr], T, a.G);
-        const int64_t slot = (seg * a.n_rr + rr) * kTileRows;
+    while (true) {
+        // ---- claim: up to 8 units, never across a row-tile boundary, smaller near the end (guided) ----
+        if (tid == 0) {
+            const int64_t left = N - (int64_t)min((unsigned int)N, s_claimed);
+            int64_t want = left / 6;
+            want = want < 1 ? 1 : (want > kStageSubs ? kStageSubs : want);
+            if (half == 0) {
+                const int64_t in_tile = a.S - (sp0 + cursor) % a.S;         // units up to the end of the row tile
+                want = min(want, in_tile);
+            } else {
+                const int64_t in_tile = (sp0 + cursor - 1) % a.S + 1;        // units back to the start of the row tile
+                want = min(want, in_tile);
+            }
+            int64_t got = 0;
+            if (left > 0 && cursor >= 0) {
+                const unsigned int t0 = atomicAdd(&s_claimed, (unsigned int)want);
+                got = (int64_t)t0 >= N ? 0 : min(want, N - (int64_t)t0);
+            }
+            s_grant[half][0] = (int)(half == 0 ? cursor : cursor - got);
+            s_grant[half][1] = (int)got;
+        }
+        half_barrier(half);  // also: everybody in this half is done with the previous staging buffers
+        const int u0 = s_grant[half][0], nsub = s_grant[half][1];
+        if (nsub == 0) break;
+        cursor = half == 0 ? cursor + nsub : cursor - nsub;
+        const int64_t lin = (int64_t)sp0 + u0;
+        const int64_t rr = rr0 + lin / a.S;
+        const int sp = (int)(lin % a.S);
+
+        if (rr != cur_rr) {  // new row tile for this half: flush the old one, load the new rows
+            flush();
+            cur_rr = rr;
+            const int r = (int)(rr / a.n_row_tiles);
+            const int I = (int)(rr % a.n_row_tiles);
+            mufu1 = a.flags[r] == 0;
+            Er = a.Es + (int64_t)r * a.Bpad;
+            Xr = a.Xs + (int64_t)r * a.Bpad;
+            Ar = a.As + (int64_t)r * a.Bpad;
+            const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
+            // Each warp owns 128 CONSECUTIVE sorted rows of the tile (lane l, k -> row 128 w + 32 k + l) and runs
+            // the class planned for ITS OWN attribute range (plan_classes_kernel).
+            const int64_t m0 = (int64_t)I * kTileRows + (int64_t)warp * kWarpRows;
+            warp_has_rows = m0 < a.n_rows;
 #pragma unroll
-        for (int k = 0; k < kTileRI; ++k) {
-            const int64_t o = slot + warp * (kTileRows / (kTileThreads / 32)) + k * 32 + lane;  // = row - tile start
-            if (valid[k]) lthread += dl[k];
-            if (GRAD) a.pgrad[o] = dg[k];
-            if (a.prow) a.prow[o] = dl[k];
+            for (int k = 0; k < kTileRI; ++k) {
+                const int64_t m = m0 + (int64_t)k * 32 + lane;
+                valid[k] = m < a.n_rows;
+                const int64_t pos = valid[k] ? (rp ? (int64_t)rp[m] : m) : 0;
+                R.e[k] = valid[k] ? Er[pos] : 1.0f;
+                R.x[k] = valid[k] ? Xr[pos] : 0.0f;
+                R.a[k] = valid[k] ? Ar[pos] : 0.0f;
+            }
         }
-        ++rr;
-        sp0 = 0;
+
+        // ---- stage the granted units (visited in the permuted order s = (s' P) mod S, see plan_classes_kernel)
+        for (int q = tid * 4; q < nsub * kSubCols; q += kTileThreads * 4) {
+            const int w = q / kSubCols;
+            const int64_t col = (((int64_t)(sp + w) * a.P) % a.S) * kSubCols + (q - w * kSubCols);
+            *reinterpret_cast<float4 *>(hse + q) = *reinterpret_cast<const float4 *>(Er + col);
+            *reinterpret_cast<float4 *>(hsx + q) = *reinterpret_cast<const float4 *>(Xr + col);
+            *reinterpret_cast<float4 *>(hsa + q) = *reinterpret_cast<const float4 *>(Ar + col);
+        }
+        half_barrier(half);
+        if (warp_has_rows) {
+            for (int w = 0; w < nsub; ++w) {
+                const int sub = w * kSubCols;
+                const int cls = (a.cls8[rr * a.S + sp + w] >> (2 * warp)) & 3;  // planned class of this warp's tile
+                if (mufu1) sweep_subchunk<true, GRAD>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg);
+                else sweep_subchunk<false, GRAD>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg);
+            }
+        }
     }
+    flush();
 
     lthread = warp_sum(lthread);
     if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = lthread;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
+        acc_t t = 0;
 #pragma unroll
-        for (int w = 0; w < kTileThreads / 32; ++w) t += sred[w];
+        for (int w = 0; w < kDuoThreads / 32; ++w) t += sred[w];
         a.lossp[c] = t;
         if (a.dbg_times) {
             unsigned long long tt;
@@ -592,23 +654,24 @@ reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int6
         const long long T = a.prefix[a.n_rr];
         const int64_t c0 = owner_of_pos(a.prefix[rr], T, a.G);
         const int64_t c1 = owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G);
+        const int64_t nslot = 2 * min(c1 - c0 + 1, (int64_t)a.max_segs);  // (segment, half) slots; unused ones are zero
         const int64_t pos = a.rowpos ? (int64_t)a.rowpos[(int64_t)r * a.n_rows + m] : m;
         const int64_t out = ((int64_t)perm[(int64_t)r * a.Bpad + pos] - row_begin) * R + r;
         if (grad_cols) {
-            double g = 0.0;
-            for (int64_t seg = 0; seg <= c1 - c0; ++seg) g += a.pgrad[(seg * a.n_rr + rr) * kTileRows + lr];
-            grad_cols[out] = (float)(g * gscale);
+            acc_t g = 0;
+            for (int64_t sl = 0; sl < nslot; ++sl) g += a.pgrad[(sl * a.n_rr + rr) * kTileRows + lr];
+            grad_cols[out] = (float)((double)g * kFixScale * gscale);
         }
         if (row_loss) {
-            double l = 0.0;
-            for (int64_t seg = 0; seg <= c1 - c0; ++seg) l += a.prow[(seg * a.n_rr + rr) * kTileRows + lr];
-            row_loss[out] = l - pad_per_row;
+            acc_t l = 0;
+            for (int64_t sl = 0; sl < nslot; ++sl) l += a.prow[(sl * a.n_rr + rr) * kTileRows + lr];
+            row_loss[out] = (double)l * kFixScale - pad_per_row;
         }
     }
     if (blockIdx.x == 0) {
         __shared__ double sh[256];
         double t = 0.0;
-        for (int64_t u = threadIdx.x; u < a.G; u += 256) t += a.lossp[u];
+        for (int64_t u = threadIdx.x; u < a.G; u += 256) t += (double)a.lossp[u] * kLossScale;  // fixed order
         sh[threadIdx.x] = t;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
@@ -643,8 +706,10 @@ static int tiles_ctas_per_sm(bool grad) {
     int &v = cache[grad ? 1 : 0];
     if (v == 0) {
         int n = 0;
-        cudaError_t e = grad ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<true>, kTileThreads, 0)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<false>, kTileThreads, 0);
+        cudaFuncSetAttribute(reg_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaError_t e = grad ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<true>, kDuoThreads, kDuoStageBytes)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<false>, kDuoThreads, kDuoStageBytes);
         if (e != cudaSuccess || n <= 0) {
             (void)cudaGetLastError();
             n = 4;
@@ -665,7 +730,7 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
     L.n_rr = (int64_t)R * L.n_row_tiles;
     L.F = L.n_rr * L.S;
     // the larger occupancy of the two kernel variants bounds the slot count for both
-    const int per_sm = 8;
+    const int per_sm = 2;  // the pair kernel runs 1 CTA (two halves) per SM, the triangle variant 2 CTAs per SM
     int64_t G = (int64_t)sm_count * per_sm;
     if (G > L.F / 4) G = L.F / 4;  // >= 4 units per CTA on average: every CTA owns at least one unit
     L.G_max = (int)(G > 0 ? G : 1);
@@ -694,9 +759,10 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
     L.off_cost8 = take(sizeof(unsigned short) * (size_t)L.F);
     L.off_combo = take(sizeof(int) * (size_t)L.n_rr);
     L.off_prefix = take(sizeof(long long) * (size_t)(L.n_rr + 1));
-    L.off_pgrad = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
-    L.off_prow = take(sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows);
-    L.off_lossp = take(sizeof(double) * (size_t)L.G_max);
+    L.slot_bytes = sizeof(acc_t) * 2 * (size_t)L.max_segs * L.n_rr * kTileRows;  // (segment, half) slots per row tile
+    L.off_pgrad = take(L.slot_bytes);
+    L.off_prow = take(L.slot_bytes);
+    L.off_lossp = take(sizeof(acc_t) * (size_t)L.G_max);
     L.off_colpart = take(tri_capable ? sizeof(float2) * (size_t)R * (size_t)colpart_size(L.n_row_tiles, L.Bpad) : 0);
     L.off_eloss = take(sizeof(double) * (size_t)(ceil_div((n_rows > 0 ? n_rows : 1) * (int64_t)R, 256)));
     L.off_dbg = take(sizeof(unsigned long long) * 2 * (size_t)L.G_max);
@@ -753,22 +819,25 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     a.cost8 = reinterpret_cast<unsigned short *>(ws + L.off_cost8);
     a.prefix = reinterpret_cast<long long *>(ws + L.off_prefix);
     int *combo_cost = reinterpret_cast<int *>(ws + L.off_combo);
-    a.pgrad = reinterpret_cast<double *>(ws + L.off_pgrad);
-    a.prow = P.row_loss_out ? reinterpret_cast<double *>(ws + L.off_prow) : nullptr;
-    a.lossp = reinterpret_cast<double *>(ws + L.off_lossp);
+    a.pgrad = reinterpret_cast<acc_t *>(ws + L.off_pgrad);
+    a.prow = P.row_loss_out ? reinterpret_cast<acc_t *>(ws + L.off_prow) : nullptr;
+    a.lossp = reinterpret_cast<acc_t *>(ws + L.off_lossp);
     a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
 
     a.colpart = nullptr; a.Pinv = 0; a.B = P.B; a.max_segs = L.max_segs;
     if (P.use_triangle && all_rows && n_rows > 0) return run_reg_tri_tail(P, L, a, perm, combo_cost, ws, st);
 
     if (n_rows > 0) {
+        // slots of a (segment, half) that processed nothing of a row tile must read as zero
+        if (want_grad) ARVAE_CUDA_TRY(cudaMemsetAsync(a.pgrad, 0, L.slot_bytes, st));
+        if (a.prow) ARVAE_CUDA_TRY(cudaMemsetAsync(a.prow, 0, L.slot_bytes, st));
         plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);
         ARVAE_LAUNCH_CHECK("plan_classes_kernel");
         plan_scan_kernel<<<1, 1024, 0, st>>>(combo_cost, L.n_rr, a.prefix);
         ARVAE_LAUNCH_CHECK("plan_scan_kernel");
         profile_begin(st);
-        if (want_grad) reg_tiles_kernel<true><<<a.G, kTileThreads, 0, st>>>(a);
-        else reg_tiles_kernel<false><<<a.G, kTileThreads, 0, st>>>(a);
+        if (want_grad) reg_tiles_kernel<true><<<a.G, kDuoThreads, kDuoStageBytes, st>>>(a);
+        else reg_tiles_kernel<false><<<a.G, kDuoThreads, kDuoStageBytes, st>>>(a);
         profile_end(st);
         ARVAE_LAUNCH_CHECK("reg_tiles_kernel");
     } else {

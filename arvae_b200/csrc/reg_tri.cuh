@@ -103,11 +103,11 @@ tri_plan_kernel(TilesArgs a, int *__restrict__ combo_cost) {
 }
 
 // Double-duty constant-sign (s_ij = -1) tile: row sums in registers, column sums to scol (fixed point).
-template <bool MUFU1, bool GRAD>
+template <bool MUFU1, bool GRAD, int ncols>
 __device__ __forceinline__ void loop_double(const RowRegs &R, const float *__restrict__ se,
-                                            const float *__restrict__ sx, float cabs, int ncols,
+                                            const float *__restrict__ sx, float cabs,
                                             unsigned int *__restrict__ scol /* [ncols][2] for these columns */,
-                                            double (&dl)[kTileRI], double (&dg)[kTileRI]) {
+                                            acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
     const int lane = threadIdx.x & 31;
     float A1[kTileRI][4], A2[kTileRI][4];
 #pragma unroll
@@ -184,18 +184,18 @@ __device__ __forceinline__ void loop_double(const RowRegs &R, const float *__res
     for (int k = 0; k < kTileRI; ++k) {
         const float S1 = (A1[k][0] + A1[k][1]) + (A1[k][2] + A1[k][3]);
         const float S2 = (A2[k][0] + A2[k][1]) + (A2[k][2] + A2[k][3]);
-        dl[k] += (double)(2.0f * ((float)ncols - S1));  // s = -1: |t - s| = 2 (1 - r)
-        if (GRAD) dg[k] += (double)(S1 - S2);            //         g / 4 = +(r - r^2)
+        acc_add(dl[k], 2.0f * ((float)ncols - S1));  // s = -1: |t - s| = 2 (1 - r)
+        if (GRAD) acc_add(dg[k], S1 - S2);            //         g / 4 = +(r - r^2)
     }
 }
 
-template <bool MUFU1, bool GRAD>
+template <bool MUFU1, bool GRAD, int ncols>
 __device__ __forceinline__ void tri_run(int code, const RowRegs &R, const float *se, const float *sx,
-                                        const float *sa, float cabs, int ncols, unsigned int *scol,
-                                        double (&dl)[kTileRI], double (&dg)[kTileRI]) {
-    if (code == kTriDouble) loop_double<MUFU1, GRAD>(R, se, sx, cabs, ncols, scol, dl, dg);
-    else if (code == kTriTie) loop_tie<MUFU1, GRAD>(R, se, sx, cabs, dl, dg, ncols);
-    else if (code == kTriGeneral) loop_general<MUFU1, GRAD>(R, se, sx, sa, cabs, dl, dg, ncols);
+                                        const float *sa, float cabs, unsigned int *scol,
+                                        acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
+    if (code == kTriDouble) loop_double<MUFU1, GRAD, ncols>(R, se, sx, cabs, scol, dl, dg);
+    else if (code == kTriTie) loop_tie<MUFU1, GRAD, ncols>(R, se, sx, cabs, dl, dg);
+    else if (code == kTriGeneral) loop_general<MUFU1, GRAD, ncols>(R, se, sx, sa, cabs, dl, dg);
 }
 
 __device__ __forceinline__ bool word_has_double(unsigned int word) {
@@ -213,7 +213,7 @@ reg_tri_kernel(TilesArgs a) {
     __shared__ unsigned int scol[kStageCols * 2];  // fixed-point column sums of the current batch (<= 1024 * 2^20 = 2^30)
     __shared__ unsigned int swords[kStageSubs];
     __shared__ int sJ[kStageSubs];
-    __shared__ double sred[kTileThreads / 32];
+    __shared__ acc_t sred[kTileThreads / 32];
     __shared__ int s_rng[4];
     __shared__ int s_scan[kTileThreads];
 
@@ -225,13 +225,13 @@ reg_tri_kernel(TilesArgs a) {
     }
     for (int q = threadIdx.x; q < kStageCols * 2; q += kTileThreads) scol[q] = 0;
     const long long T = a.prefix[a.n_rr];
-    find_unit(a, ceil_share(c, T, a.G), s_rng, s_scan);
-    find_unit(a, ceil_share(c + 1, T, a.G), s_rng + 2, s_scan);
+    find_unit<kTileThreads>(a, ceil_share(c, T, a.G), s_rng, s_scan);
+    find_unit<kTileThreads>(a, ceil_share(c + 1, T, a.G), s_rng + 2, s_scan);
     int64_t rr = s_rng[0];
     int sp0 = s_rng[1];
     const int64_t rr_end = s_rng[2];
     const int sp_end = s_rng[3];
-    double lthread = 0.0;
+    acc_t lthread = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     while (rr < rr_end || (rr == rr_end && sp0 < sp_end)) {
@@ -250,7 +250,7 @@ reg_tri_kernel(TilesArgs a) {
         const bool warp_has_rows = m0 < a.n_rows;
         RowRegs R;
         bool valid[kTileRI];
-        double dl[kTileRI], dg[kTileRI];
+        acc_t dl[kTileRI], dg[kTileRI];
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
             const int64_t m = m0 + (int64_t)k * 32 + lane;
@@ -259,8 +259,8 @@ reg_tri_kernel(TilesArgs a) {
             R.e[k] = valid[k] ? Er[pos] : __int_as_float(0x7f800000);
             R.x[k] = valid[k] ? Xr[pos] : __int_as_float(0x7f800000);
             R.a[k] = valid[k] ? Ar[pos] : 0.0f;
-            dl[k] = 0.0;
-            dg[k] = 0.0;
+            dl[k] = 0;
+            dg[k] = 0;
         }
 
         for (int sp = s0; sp < s1 + kStageSubs; sp += kStageSubs) {
@@ -300,17 +300,17 @@ reg_tri_kernel(TilesArgs a) {
                     const int c0 = code & 3, c1 = code >> 2;
                     const int sub = w * kSubCols;
                     if (c0 == c1) {
-                        if (mufu1) tri_run<true, GRAD>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, kSubCols, scol + sub * 2, dl, dg);
-                        else tri_run<false, GRAD>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, kSubCols, scol + sub * 2, dl, dg);
+                        if (mufu1) tri_run<true, GRAD, kSubCols>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, scol + sub * 2, dl, dg);
+                        else tri_run<false, GRAD, kSubCols>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, scol + sub * 2, dl, dg);
                     } else {
                         if (mufu1) {
-                            tri_run<true, GRAD>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, kHalfCols, scol + sub * 2, dl, dg);
-                            tri_run<true, GRAD>(c1, R, se + sub + kHalfCols, sx + sub + kHalfCols, sa + sub + kHalfCols, a.cabs,
-                                                kHalfCols, scol + (sub + kHalfCols) * 2, dl, dg);
+                            tri_run<true, GRAD, kHalfCols>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, scol + sub * 2, dl, dg);
+                            tri_run<true, GRAD, kHalfCols>(c1, R, se + sub + kHalfCols, sx + sub + kHalfCols, sa + sub + kHalfCols, a.cabs,
+                                                           scol + (sub + kHalfCols) * 2, dl, dg);
                         } else {
-                            tri_run<false, GRAD>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, kHalfCols, scol + sub * 2, dl, dg);
-                            tri_run<false, GRAD>(c1, R, se + sub + kHalfCols, sx + sub + kHalfCols, sa + sub + kHalfCols, a.cabs,
-                                                 kHalfCols, scol + (sub + kHalfCols) * 2, dl, dg);
+                            tri_run<false, GRAD, kHalfCols>(c0, R, se + sub, sx + sub, sa + sub, a.cabs, scol + sub * 2, dl, dg);
+                            tri_run<false, GRAD, kHalfCols>(c1, R, se + sub + kHalfCols, sx + sub + kHalfCols, sa + sub + kHalfCols, a.cabs,
+                                                            scol + (sub + kHalfCols) * 2, dl, dg);
                         }
                     }
                 }
@@ -325,9 +325,9 @@ reg_tri_kernel(TilesArgs a) {
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
             const int64_t o = slot + warp * kWarpRowsT + k * 32 + lane;
-            if (valid[k]) lthread += dl[k];
-            if (GRAD) a.pgrad[o] = valid[k] ? dg[k] : 0.0;
-            if (a.prow) a.prow[o] = valid[k] ? dl[k] : 0.0;
+            if (valid[k]) lthread += dl[k] >> kLossShift;
+            if (GRAD) a.pgrad[o] = valid[k] ? dg[k] : 0;
+            if (a.prow) a.prow[o] = valid[k] ? dl[k] : 0;
         }
         ++rr;
         sp0 = 0;
@@ -337,7 +337,7 @@ reg_tri_kernel(TilesArgs a) {
     if (lane == 0) sred[warp] = lthread;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
+        acc_t t = 0;
 #pragma unroll
         for (int w = 0; w < kTileThreads / 32; ++w) t += sred[w];
         a.lossp[c] = t;
@@ -367,11 +367,12 @@ reg_tri_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, double
         const int64_t c0 = owner_of_pos(a.prefix[rr], T, a.G);
         const int64_t c1 = owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G);
         const int64_t nseg = min(c1 - c0 + 1, (int64_t)a.max_segs);
-        double g = 0.0, l = 0.0;
+        acc_t gi = 0, li = 0;
         for (int64_t seg = 0; seg < nseg; ++seg) {
-            if (grad_cols) g += a.pgrad[(seg * a.n_rr + rr) * kTileRows + lr];
-            if (row_loss) l += a.prow[(seg * a.n_rr + rr) * kTileRows + lr];
+            if (grad_cols) gi += a.pgrad[(seg * a.n_rr + rr) * kTileRows + lr];
+            if (row_loss) li += a.prow[(seg * a.n_rr + rr) * kTileRows + lr];
         }
+        const double g = (double)gi * kFixScale, l = (double)li * kFixScale;
         // column side
         const int64_t J = q / kSubCols;
         const int half = (int)((q / kHalfCols) & 1);
@@ -411,12 +412,12 @@ reg_tri_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, double
 }
 
 __global__ void __launch_bounds__(256)
-reg_tri_finish_kernel(const double *__restrict__ lossp, int64_t n_lossp, const double *__restrict__ eloss,
+reg_tri_finish_kernel(const acc_t *__restrict__ lossp, int64_t n_lossp, const double *__restrict__ eloss,
                       int64_t n_eloss, double pad_total, double lscale, double *__restrict__ loss_out,
                       float *__restrict__ loss_f32_out) {
     __shared__ double sh[256];
     double t = 0.0;
-    for (int64_t u = threadIdx.x; u < n_lossp; u += 256) t += lossp[u];
+    for (int64_t u = threadIdx.x; u < n_lossp; u += 256) t += (double)lossp[u] * kLossScale;
     for (int64_t u = threadIdx.x; u < n_eloss; u += 256) t += eloss[u];
     sh[threadIdx.x] = t;
     __syncthreads();
@@ -476,8 +477,8 @@ static int run_reg_tri_tail(const RegProblem &P, const SortedLayout &L, TilesArg
     const int64_t n_eblocks = work > 0 ? ceil_div(work, 256) : 1;
 
     // slots of CTAs that own no unit of a row tile must read as zero
-    ARVAE_CUDA_TRY(cudaMemsetAsync(a.pgrad, 0, sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows, st));
-    if (a.prow) ARVAE_CUDA_TRY(cudaMemsetAsync(a.prow, 0, sizeof(double) * (size_t)L.max_segs * L.n_rr * kTileRows, st));
+    ARVAE_CUDA_TRY(cudaMemsetAsync(a.pgrad, 0, L.slot_bytes, st));
+    if (a.prow) ARVAE_CUDA_TRY(cudaMemsetAsync(a.prow, 0, L.slot_bytes, st));
     tri_plan_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);
     ARVAE_LAUNCH_CHECK("tri_plan_kernel");
     plan_scan_kernel<<<1, 1024, 0, st>>>(combo_cost, L.n_rr, a.prefix);

@@ -7,7 +7,8 @@ import numpy as np, torch
 from arvae_b200 import _lib, ops, synth
 lib = _lib.load()
 lib.arvae_debug_times_offset.restype = ctypes.c_int64
-lib.arvae_debug_times_offset.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+lib.arvae_debug_times_offset.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]
+ALGO = int(os.environ.get("ALGO", "2"))
 c = synth.make_case("c4_mnist_b65536")
 z, lab = c["z"].cuda(), c["labels"].cuda()
 dims = c["reg_dims"]; R = len(dims); B = c["B"]
@@ -15,9 +16,9 @@ packed = ops.pack_columns(z, lab, dims, dims)
 for shards in (1,):
     n = B // shards
     g = ctypes.c_int32()
-    off = lib.arvae_debug_times_offset(B, n, R, ctypes.byref(g))
+    off = lib.arvae_debug_times_offset(B, n, R, ALGO, ctypes.byref(g))
     lib.arvae_reg_loss_workspace_bytes_algo.restype = ctypes.c_size_t
-    ws_bytes = int(lib.arvae_reg_loss_workspace_bytes_algo(B, n, R, 3))
+    ws_bytes = int(lib.arvae_reg_loss_workspace_bytes_algo(B, n, R, ALGO))
     ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
     loss = torch.empty((), dtype=torch.float64, device="cuda")
     gc = torch.empty((n, R), dtype=torch.float32, device="cuda")

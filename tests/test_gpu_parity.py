@@ -230,7 +230,7 @@ def test_row_blocks_add_up_and_rows_are_bitwise_identical(ab, algo):
     assert_loss_close(full_loss.item(), g["loss"])
     # per-row sums add up to the loss
     tot = full_rows.sum().item() * gamma / (B * B)
-    assert abs(tot - full_loss.item()) <= 1e-12 * abs(tot)
+    assert abs(tot - full_loss.item()) <= 1e-9 * abs(tot)
 
 
 def test_run_to_run_bitwise_reproducible(ab):
@@ -275,7 +275,7 @@ def test_c4_full_size_row_samples_and_properties(ab, oracle_mod, algo):
             assert abs(grad_cols[i, r] - c["gamma"] * g[0]) <= 1e-5 * scale[r], (i, r)
     # (2) the loss is the sum of the row sums, and lies in [0, 2*gamma*R]
     tot = row_loss.sum() * c["gamma"] / (float(B) * float(B))
-    assert abs(tot - loss64.item()) <= 1e-12 * tot
+    assert abs(tot - loss64.item()) <= 1e-9 * tot  # per-CTA loss partials carry 2^-24 fixed point
     assert 0.0 < loss64.item() < 2.0 * c["gamma"] * len(dims)
     # (3) antisymmetry: gradients of a pairwise-difference loss sum to zero over the batch
     colsum = grad_cols.astype(np.float64).sum(axis=0)
