@@ -10,9 +10,12 @@
 
 namespace arvae {
 
-constexpr int kSortChunk = 4096;   // keys sorted per CTA in shared memory (32 KiB): small enough that a
-                                   // 65536-key x 6-dim sort spreads over 96 CTAs
-constexpr int kSortThreads = 512;  // 8 keys per thread
+#ifndef ARVAE_SORT_CHUNK
+#define ARVAE_SORT_CHUNK 2048
+#endif
+constexpr int kSortChunk = ARVAE_SORT_CHUNK;     // keys sorted per CTA in shared memory: small enough that a
+                                                 // 65536-key x 6-dim sort spreads over every SM (192 CTAs)
+constexpr int kSortThreads = kSortChunk / 8;     // 8 keys per thread
 
 __device__ __forceinline__ unsigned int float_to_sortable(float a) {
     if (a != a) return 0xFFFFFFFEu;  // every NaN: one class, after +inf (0xFF800000)
@@ -129,13 +132,28 @@ __device__ __forceinline__ void smem_steps_down_to_256(unsigned long long *s, in
 
 // Sorts each kSortChunk-sized chunk in shared memory: all stages with k <= kSortChunk when
 // `k_only` == 0, or only the tail j = kSortChunk/2 .. 1 of stage `k_only` when merging.
+// With `lab` != null (first pass, k_only == 0) the keys are built on the fly from the label column instead of
+// being read back (saves the make_keys launch and a round trip through memory).
 __global__ void __launch_bounds__(kSortThreads)
-bitonic_local_kernel(unsigned long long *__restrict__ keys, int64_t N, int64_t k_only) {
+bitonic_local_kernel(unsigned long long *__restrict__ keys, int64_t N, int64_t k_only,
+                     const float *__restrict__ lab, int64_t lrs, int64_t lcs, RegDims dims, int64_t B) {
     extern __shared__ __align__(16) unsigned long long s[];
     unsigned long long *base = keys + (int64_t)blockIdx.y * N + (int64_t)blockIdx.x * kSortChunk;
     const int64_t g0 = (int64_t)blockIdx.x * kSortChunk;  // global index of s[0] within this dim
     const int n = (int)min((int64_t)kSortChunk, N);       // N is a power of two >= 256
-    for (int i = threadIdx.x; i < n; i += kSortThreads) s[i] = base[i];
+    if (lab) {
+        for (int i = threadIdx.x; i < n; i += kSortThreads) {
+            const int64_t j = g0 + i;
+            unsigned long long k = ~0ull;  // padding sorts last
+            if (j < B) {
+                const float a = __ldg(lab + j * lrs + (int64_t)dims.lcol[blockIdx.y] * lcs);
+                k = ((unsigned long long)float_to_sortable(a) << 32) | (unsigned long long)(unsigned int)j;
+            }
+            s[i] = k;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += kSortThreads) s[i] = base[i];
+    }
     __syncthreads();
     if (k_only == 0) {
         smem_round_tail(s, n, g0, 2, min(256, n));  // stages 2..256 entirely in registers / shuffles
@@ -201,13 +219,10 @@ int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dim
                                             (int)(kSortChunk * sizeof(unsigned long long))));
         attr_set = true;
     }
-    dim3 g1((unsigned)ceil_div(N, 256), (unsigned)R);
-    make_keys_kernel<<<g1, 256, 0, st>>>(lab, lrs, lcs, dims, B, N, keys);
-    ARVAE_LAUNCH_CHECK("make_keys_kernel");
     const int64_t chunks = N > kSortChunk ? N / kSortChunk : 1;
     const size_t smem = (size_t)(N < kSortChunk ? N : kSortChunk) * sizeof(unsigned long long);
     dim3 gl((unsigned)chunks, (unsigned)R);
-    bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, 0);
+    bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, 0, lab, lrs, lcs, dims, B);
     ARVAE_LAUNCH_CHECK("bitonic_local_kernel");
     for (int64_t k = 2 * (int64_t)kSortChunk; k <= N; k <<= 1) {
         int64_t j = k >> 1;
@@ -220,7 +235,7 @@ int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dim
             ARVAE_LAUNCH_CHECK("bitonic_global_kernel");
             j >>= steps;
         }
-        bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, k);
+        bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, k, nullptr, 0, 0, dims, B);
         ARVAE_LAUNCH_CHECK("bitonic_local_kernel(merge)");
     }
     return 0;
