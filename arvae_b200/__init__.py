@@ -7,6 +7,7 @@ forms, on top of the C ABI in ``include/arvae_b200.h`` (``csrc/libarvae_b200.so`
 from __future__ import annotations
 
 from . import _lib  # noqa: F401
+from . import graphs  # noqa: F401
 from .ops import (ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, compute_kld_loss, compute_reg_loss, latent_head, mufu_per_pair,
                   reg_loss_fused, reg_loss_rows, reg_loss_sign, reparam_kld_reg, reparametrize, sign_matrix,
                   attr_argsort, pack_columns)

@@ -55,6 +55,14 @@ for name, B, kind in cases:
     iters = 50 if c["B"] <= 8192 else (10 if c["B"] <= 65536 else 3)
     row = {"config": name, "B": c["B"], "R": len(dims), "labels": kind, "delta": delta,
            "ours_fused_ms": timeit(ours, iters), "ours_per_dim_calls_ms": timeit(per_dim_calls, iters)}
+    if c["B"] <= 8192:  # launch-latency-bound sizes: CUDA-graph replay of the same forward + backward
+        from arvae_b200 import graphs
+        step = graphs.graphed_reg_loss(c["B"], z.shape[1], lab.shape[1], dims, gamma, delta)
+
+        def graphed():
+            zz = z.detach().requires_grad_(True)
+            step(zz, lab).backward()
+        row["ours_graphed_ms"] = timeit(graphed, iters)
     if c["B"] <= 8192:
         try:
             row["stock_torch_cuda_ms"] = timeit(stock, 5)

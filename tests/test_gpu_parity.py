@@ -451,3 +451,46 @@ def test_mufu_range_guard_falls_back_to_two_mufu_form(ab, oracle_mod):
     assert_grad_close(zc.grad.cpu().numpy(), ref_grad)
     # delta = 10 (the MeasureVAE setting): every N(0,1) column trips the guard
     assert set(ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 2), 1.0, 10.0)) == {2.0}
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph capture (small, launch-latency-bound batches)
+# ------------------------------------------------------------------------------------------------
+def test_graph_captured_reg_loss_matches_eager(ab):
+    from arvae_b200 import graphs
+    g = golden("reg_c1_mnist_b64")
+    dims = tuple(int(d) for d in g["reg_dims"])
+    B, Z = g["z"].shape
+    step = graphs.graphed_reg_loss(B, Z, g["labels"].shape[1], dims, float(g["gamma"]), float(g["delta"]))
+    for trial in range(3):  # replays must pick up new input contents
+        gen = torch.Generator().manual_seed(trial)
+        z = (dev(g["z"]) if trial == 0 else torch.randn(B, Z, generator=gen).cuda()).requires_grad_(True)
+        labels = dev(g["labels"]) if trial == 0 else torch.randn(B, g["labels"].shape[1], generator=gen).cuda()
+        loss = step(z, labels)
+        loss.backward()
+        z2 = z.detach().clone().requires_grad_(True)
+        ref = ab.reg_loss_fused(z2, labels, dims, float(g["gamma"]), float(g["delta"]))
+        ref.backward()
+        assert torch.equal(loss.detach(), ref.detach())
+        assert torch.equal(z.grad, z2.grad)
+        if trial == 0:
+            assert_loss_close(loss.item(), g["loss"])
+            assert_grad_close(z.grad.cpu().numpy(), g["grad_z"])
+
+
+def test_graph_captured_latent_head_matches_eager(ab):
+    from arvae_b200 import graphs
+    g = golden("head_c3_measure_b2048")
+    dims = tuple(int(d) for d in g["reg_dims"])
+    B, Z = g["loc"].shape
+    head = graphs.graphed_latent_head(B, Z, g["labels"].shape[1], dims, float(g["beta"]), float(g["capacity"]),
+                                      float(g["gamma"]), float(g["delta"]))
+    loc = dev(g["loc"]).requires_grad_(True)
+    scale = torch.exp(torch.from_numpy(g["log_std"])).cuda().requires_grad_(True)
+    z, kld, reg = head(loc, scale, dev(g["eps"]), dev(g["labels"]))
+    (kld + reg).backward()
+    assert np.array_equal(z.detach().cpu().numpy(), g["z_tilde"])
+    assert_loss_close(kld.item(), g["kld_loss"])
+    assert_loss_close(reg.item(), g["reg_loss"])
+    assert_grad_close(loc.grad.cpu().numpy(), g["grad_loc"])
+    assert_grad_close(scale.grad.cpu().numpy(), g["grad_scale"])
