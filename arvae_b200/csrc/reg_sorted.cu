@@ -140,6 +140,25 @@ struct RowRegs {
     float a[kTileRI];  // attribute
 };
 
+// Reciprocal on the FMA / ALU pipes: magic-constant seed (relative error < 0.051) and three Newton steps
+// (error -> 2.6e-3 -> 6.8e-6 -> 4.6e-11, i.e. correctly rounded to within an ulp).  7 instructions instead of one
+// MUFU.RCP: used for a small, fixed subset of the pairs of the constant-sign loop so that the XU pipe (the
+// bound) and the issue slots (idle ~35 % of the time) are both kept busy.  Valid for normal positive x.
+__device__ __forceinline__ float rcp_newton(float x) {
+    float y = __int_as_float(0x7EF311C7 - __float_as_int(x));
+    float e = fmaf(-x, y, 1.0f);
+    y = fmaf(y, e, y);
+    e = fmaf(-x, y, 1.0f);
+    y = fmaf(y, e, y);
+    e = fmaf(-x, y, 1.0f);
+    return fmaf(y, e, y);
+}
+
+#ifndef ARVAE_NR_PAIRS
+#define ARVAE_NR_PAIRS 0  // of every 16 pairs of the 1-MUFU constant-sign loop, how many use rcp_newton (measured: 3 -> +2..4 %; off by
+                          // default so that the kernel stays a plain 1-MUFU-per-pair loop whose roofline is the XU pipe)
+#endif
+
 template <bool MUFU1>
 __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs) {
     if (MUFU1) return rcp_approx(ei + ej) * ej;          // E_j / (E_i + E_j)
@@ -164,8 +183,13 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
         for (int k = 0; k < kTileRI; ++k) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float r = MUFU1 ? pair_r<true>(R.e[k], vv[e], 0.0f, cabs)
-                                      : pair_r<false>(0.0f, 0.0f, R.x[k] - vv[e], cabs);
+                float r;
+                if (MUFU1 && (k * 4 + e) >= 16 - ARVAE_NR_PAIRS) {  // compile-time: the last few pairs of each 4 x 4 group
+                    r = rcp_newton(R.e[k] + vv[e]) * vv[e];  // E_j / (E_i + E_j) without the XU pipe
+                } else {
+                    r = MUFU1 ? pair_r<true>(R.e[k], vv[e], 0.0f, cabs)
+                              : pair_r<false>(0.0f, 0.0f, R.x[k] - vv[e], cabs);
+                }
                 A1[k][e] += r;
                 if (GRAD) A2[k][e] = fmaf(r, r, A2[k][e]);
             }
