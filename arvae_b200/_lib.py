@@ -46,6 +46,7 @@ SIGNATURES = {
     "arvae_pack_columns_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _c_i32p, _c_i32p, _i32, _i64, _vp, _vp]),
     "arvae_attr_argsort_workspace_bytes": (_sz, [_i64]),
     "arvae_attr_argsort_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "arvae_measure_attributes_i64": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp]),
     "arvae_reg_sign_matrix_i8": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "arvae_launch_count": (_i64, [ctypes.c_int]),
     "arvae_profile_enable": (None, [ctypes.c_int]),

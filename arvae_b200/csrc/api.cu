@@ -413,6 +413,17 @@ int arvae_attr_argsort_f32(const float *labels_dev, int64_t lab_stride, int64_t 
     return run_extract_perm(keys, B, perm_out_dev, st);
 }
 
+int arvae_measure_attributes_i64(const int64_t *measures_dev, int64_t B, int64_t T, int64_t row_stride,
+                                 const int32_t *lut_dev, int64_t V, const float *rhy_weights_dev, float *out_dev,
+                                 void *stream) {
+    if (B < 0 || T <= 0 || V <= 0 || (B > 0 && (!measures_dev || !lut_dev || !rhy_weights_dev || !out_dev))) {
+        set_error("bad argument to measure_attributes");
+        return ARVAE_E_BADARG;
+    }
+    return run_measure_attributes(reinterpret_cast<const long long *>(measures_dev), B, T, row_stride, lut_dev, V,
+                                  rhy_weights_dev, out_dev, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
                              int8_t *out_dev, void *stream) {
     if (B < 0 || (B > 0 && (!labels_dev || !out_dev))) {

@@ -81,6 +81,9 @@ int run_latent_head_bwd(const float *loc, const float *scale, const float *eps, 
                         float kscale, const float *kcoef, const float *gkld, int64_t B, int64_t Z,
                         float *dloc, float *dscale, cudaStream_t st);
 
+int run_measure_attributes(const long long *measures, int64_t B, int64_t T, int64_t row_stride, const int *lut,
+                           int64_t V, const float *weights, float *out, cudaStream_t st);
+
 int sm_count();
 
 }  // namespace arvae

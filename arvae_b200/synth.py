@@ -101,3 +101,40 @@ def make_latent_head(B: int, Z: int, seed: int) -> Tuple[torch.Tensor, torch.Ten
     log_std = -1.0 + 0.25 * torch.randn(B, Z, generator=g)
     eps = torch.randn(B, Z, generator=g)
     return loc, log_std, eps
+
+
+def music_vocabulary():
+    """A note dictionary shaped like the Bach / folk bar datasets': five special symbols and pitch names."""
+    names = []
+    for octave in (3, 4, 5):
+        for step in ("C", "C#", "D", "E-", "E", "F", "F#", "G", "A-", "A", "B-", "B"):
+            names.append(f"{step}{octave}")
+    symbols = ["__", "START", "END", "rest", None] + names
+    note2index = {s: i for i, s in enumerate(symbols)}
+    index2note = {i: s for s, i in note2index.items()}
+    return note2index, index2note
+
+
+def make_measures(B: int, seed: int, T: int = 24) -> torch.Tensor:
+    """[B, T] int64 bars: note onsets followed by slurs, some rests, a few START / END / None paddings,
+    plus empty and single-note bars (the reference's special cases)."""
+    g = _gen(seed)
+    note2index, _ = music_vocabulary()
+    n_special = 5
+    V = len(note2index)
+    m = torch.full((B, T), note2index["__"], dtype=torch.int64)
+    onset = torch.rand(B, T, generator=g) < 0.35
+    pitch = torch.randint(n_special, V, (B, T), generator=g)
+    m[onset] = pitch[onset]
+    rest = (torch.rand(B, T, generator=g) < 0.08) & ~onset
+    m[rest] = note2index["rest"]
+    pad = torch.rand(B, generator=g) < 0.1
+    m[pad, 0] = note2index["START"]
+    m[pad, -1] = note2index["END"]
+    nonebar = torch.rand(B, generator=g) < 0.05
+    m[nonebar, 3] = note2index[None]
+    if B > 3:
+        m[0, :] = note2index["__"]                       # no notes at all
+        m[1, :] = note2index["__"]; m[1, 5] = n_special + 7   # exactly one note
+        m[2, :] = note2index["rest"]
+    return m

@@ -184,6 +184,18 @@ ARVAE_API int arvae_attr_argsort_f32(const float *labels_dev, int64_t lab_stride
                                      int32_t *perm_out_dev, void *workspace_dev,
                                      size_t workspace_bytes, void *stream);
 
+/*
+ * The four musical attributes the MeasureVAE trainer regularises (reference
+ * data/dataloaders/bar_dataset.py:338-500, order of measurevae/measure_vae_trainer.py:15-20):
+ * out[b] = { rhy_complexity, pitch_range, note_density, contour } for measure b.
+ *   measures_dev [B, T] int64 note indices (row stride in elements); lut_dev [V] int32: MIDI pitch (>= 0) of a
+ *   note symbol, or -1 slur, -2 rest, -3 None, -4 START, -5 END; rhy_weights_dev [T] float (RHY_COMPLEXITY_COEFFS);
+ *   out_dev [B, 4] float.
+ */
+ARVAE_API int arvae_measure_attributes_i64(const int64_t *measures_dev, int64_t B, int64_t T,
+                                           int64_t row_stride, const int32_t *lut_dev, int64_t V,
+                                           const float *rhy_weights_dev, float *out_dev, void *stream);
+
 /* s[i*B+j] = sign(a_i - a_j) as int8, for parity tests at small B (same compare the kernels use). */
 ARVAE_API int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
                              int8_t *out_dev, void *stream);

@@ -80,6 +80,36 @@ def reg_case(Trainer, name, z, labels, reg_dims, gamma, delta, per_dim=True):
          gamma=np.float64(gamma), delta=np.float64(delta), loss=loss, grad_z=z.grad, **extra)
 
 
+def music_attribute_fixture():
+    """Runs BarDataset.get_* of the unmodified reference on synthetic bars.  music21 is not installed: it is
+    stubbed in sys.modules, with ``music21.pitch.Pitch(name).midi`` implemented by the standard pitch-name rule
+    (arvae_b200.music.midi_from_pitch_name) -- the only music21 behaviour these four methods use."""
+    from arvae_b200 import music, synth
+
+    class Pitch:
+        def __init__(self, name):
+            self.midi = music.midi_from_pitch_name(name)
+
+    m21 = types.ModuleType("music21")
+    for sub in ("meter", "abcFormat", "note", "pitch", "interval", "stream", "corpus", "converter", "expressions",
+                "duration", "tempo", "key", "metadata", "instrument"):
+        mod = types.ModuleType("music21." + sub)
+        setattr(m21, sub, mod)
+        sys.modules["music21." + sub] = mod
+    m21.abcFormat.ABCHandlerException = Exception
+    m21.pitch.Pitch = Pitch
+    sys.modules["music21"] = m21
+    from data.dataloaders.bar_dataset import BarDataset  # the reference class, unmodified
+
+    note2index, index2note = synth.music_vocabulary()
+    fake_self = types.SimpleNamespace(note2index_dicts=note2index, index2note_dicts=index2note)
+    measures = synth.make_measures(257, seed=2024)
+    cols = [BarDataset.get_rhy_complexity(fake_self, measures), BarDataset.get_pitch_range_in_measure(fake_self, measures),
+            BarDataset.get_note_density_in_measure(fake_self, measures), BarDataset.get_contour(fake_self, measures)]
+    attrs = torch.stack([c.float().cpu() for c in cols], dim=1)  # MUSIC_REG_TYPE order
+    save("music_attrs", measures=measures, attrs=attrs)
+
+
 def main():
     torch.set_num_threads(8)
     Trainer, MnistVAE = import_reference()
@@ -199,6 +229,9 @@ def main():
     k.sum().backward()
     save("kld_c1_capacity_tensor", loc=loc, scale=scale, beta=np.float64(4.0), capacity=cap_t,
          kld_loss=k, grad_loc=loc.grad, grad_scale=scale.grad)
+
+    # ---- musical attribute extractors (data/dataloaders/bar_dataset.py:338-500), reference method bodies ----
+    music_attribute_fixture()
 
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write("Golden vectors produced by tests/golden/make_golden.py from the unmodified reference\n"
