@@ -725,9 +725,17 @@ static int golden_stride(int S) {  // integer nearest 0.618 S that is coprime to
     return 1;
 }
 
+static int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return dev;
+}
+
+// CTAs of the pair kernel that fit one SM (1 with its 512 threads x 128 registers); also opts the kernel into
+// 48 KiB of dynamic shared memory.  Function attributes are per device: cached per (device, variant).
 static int tiles_ctas_per_sm(bool grad) {
-    static int cache[2] = {0, 0};
-    int &v = cache[grad ? 1 : 0];
+    static int cache[64][2] = {};
+    int &v = cache[current_device_slot()][grad ? 1 : 0];
     if (v == 0) {
         int n = 0;
         cudaFuncSetAttribute(reg_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
@@ -736,7 +744,7 @@ static int tiles_ctas_per_sm(bool grad) {
                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<false>, kDuoThreads, kDuoStageBytes);
         if (e != cudaSuccess || n <= 0) {
             (void)cudaGetLastError();
-            n = 4;
+            n = 1;
         }
         v = n;
     }

@@ -433,8 +433,8 @@ reg_tri_finish_kernel(const acc_t *__restrict__ lossp, int64_t n_lossp, const do
 }
 
 static int tri_ctas_per_sm(bool grad) {
-    static int cache[2] = {0, 0};
-    int &v = cache[grad ? 1 : 0];
+    static int cache[64][2] = {};
+    int &v = cache[current_device_slot()][grad ? 1 : 0];
     if (v == 0) {
         int n = 0;
         cudaError_t e = grad ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tri_kernel<true>, kTileThreads, 0)

@@ -213,12 +213,7 @@ static void launch_global(unsigned long long *keys, int64_t N, int R, int64_t k,
 // keys[r][0..N) <- sorted (ascending) attribute keys of dim r; N = sort_padded_size(B).
 int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, int64_t B,
                   int64_t N, unsigned long long *keys, cudaStream_t st) {
-    static bool attr_set = false;  // benign race: idempotent
-    if (!attr_set) {
-        ARVAE_CUDA_TRY(cudaFuncSetAttribute(bitonic_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(kSortChunk * sizeof(unsigned long long))));
-        attr_set = true;
-    }
+    static_assert(kSortChunk * sizeof(unsigned long long) <= 48 * 1024, "fits the default dynamic shared memory limit");
     const int64_t chunks = N > kSortChunk ? N / kSortChunk : 1;
     const size_t smem = (size_t)(N < kSortChunk ? N : kSortChunk) * sizeof(unsigned long long);
     dim3 gl((unsigned)chunks, (unsigned)R);
