@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 dense, 2 sorted")
     ap.add_argument("--batch", type=int, default=0, help="override B (parity/scaling sweeps; 0 = config C4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the device-resident step as CUDA graphs (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -242,10 +243,26 @@ def main():
     lab_dev = lab_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    graphed = None
+    if args.graph:
+        # The whole step (forward: [pack, all-gather,] sort, plan, pair kernel, epilogue [, all-reduce]; backward:
+        # gradient scatter) captured once and replayed: same kernels, same inputs-per-step, no launch gaps.
+        try:
+            from arvae_b200 import graphs
+            if world == 1:
+                graphed = graphs.graphed_reg_loss(n_local, Z, A, dims, gamma, delta, device=dev, algo=args.algo)
+            else:
+                graphed = graphs.graphed_reg_loss_sharded(n_local, Z, A, dims, gamma, delta, device=dev, algo=args.algo)
+        except Exception as e:  # capture not possible here: run eagerly and say so
+            print(f"bench.py: CUDA-graph capture failed ({e}); running eagerly", file=sys.stderr)
+            graphed = None
+
     def step_device():
         """One step with inputs resident in HBM: loss + dL/dz for this rank's rows."""
         z = z_dev.detach().requires_grad_(True)
-        if world == 1:
+        if graphed is not None:
+            loss = graphed(z, lab_dev)
+        elif world == 1:
             loss = arvae_b200.reg_loss_fused(z, lab_dev, dims, gamma, delta, algo=args.algo)
         else:
             loss = adist.reg_loss_sharded(z, lab_dev, dims, gamma, delta, algo=args.algo)
@@ -393,7 +410,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "B": B, "Z": Z, "R": R, "gamma": gamma, "delta": delta,
                    "pairs_per_step": pairs, "parallelism": f"row-block x{world}" if world > 1 else "single GPU",
-                   "algo": args.algo,
+                   "algo": args.algo, "cuda_graph": graphed is not None,
                    "l2_flush": "256 MiB memset between the timed steps (each step has its own CUDA event pair; the "
                                "flush is outside the per-step intervals; inputs are ~6 MB, far below L2)",
                    "ms_per_step_incl_flush": ms_bracket / args.steps},
