@@ -8,6 +8,9 @@ forward + backward can be captured once and replayed as one graph launch:
     step = arvae_b200.graphs.graphed_reg_loss(B, Z, A, reg_dims, gamma, factor)
     loss = step(z, labels)          # z requires grad; loss.backward() replays the captured backward
 
+Only single-GPU calls are offered: capturing the NCCL collectives of ``distributed.reg_loss_sharded`` through
+``make_graphed_callables`` deadlocked on the 2-GPU box, and at large batches replay gains nothing anyway.
+
 Shapes, reg dims, gamma and factor are baked into the graph (they are constants of a training run);
 ``z`` and ``labels`` contents are free.  Plumbing only: the capture itself is
 ``torch.cuda.make_graphed_callables``.
@@ -51,18 +54,3 @@ def graphed_latent_head(B: int, Z: int, A: int, reg_dims: Sequence[int], beta: f
     lab = torch.randn(B, A, device=device)
     return torch.cuda.make_graphed_callables(fn, (loc, scale, eps, lab), allow_unused_input=True)
 
-
-def graphed_reg_loss_sharded(n_local: int, Z: int, A: int, reg_dims: Sequence[int], gamma: float, factor: float = 1.0,
-                             device="cuda", group=None, algo: int = ops.ALGO_AUTO):
-    """Graph-captured row-block sharded loss (``distributed.reg_loss_sharded``): pack, NCCL all-gather, sort, plan,
-    pair kernel, epilogue and NCCL all-reduce replay as one graph launch per rank (and one more for the backward).
-    Every rank must build and call it collectively."""
-    from . import distributed as adist
-    dims = tuple(int(d) for d in reg_dims)
-
-    def fn(z_local, labels_local):
-        return adist.reg_loss_sharded(z_local, labels_local, dims, gamma, factor, group=group, algo=algo)
-
-    z0 = torch.randn(n_local, Z, device=device, requires_grad=True)
-    l0 = torch.randn(n_local, A, device=device)
-    return torch.cuda.make_graphed_callables(fn, (z0, l0), allow_unused_input=True)
