@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from . import _lib  # noqa: F401
 from . import graphs  # noqa: F401
+from . import music  # noqa: F401
 from .ops import (ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, ALGO_TRIANGLE, compute_kld_loss, compute_reg_loss, latent_head, mufu_per_pair,
                   reg_loss_fused, reg_loss_rows, reg_loss_sign, reparam_kld_reg, reparametrize, sign_matrix,
                   attr_argsort, pack_columns)
