@@ -21,9 +21,11 @@
 //    difference xs_i - xs_j of the (sign-adjusted) latents, never from the approximated tanh: near
 //    t = 0 the factor (1 - t^2) is maximal and abs-backward's sgn(0) = 0 must hold exactly for
 //    equal latents (the diagonal, duplicated samples).
-//  * work is split into fine units (row tile, 256-column sub-chunk) laid out linearly and divided
-//    EVENLY over a persistent grid (one contiguous range per CTA), so there is no wave tail; row
-//    partials go to a deterministic (segment, row tile) slot and are reduced in fixed order.
+//  * work is cut into units (1024-row tile, 256-column sub-chunk), visited in a permuted column order;
+//    a planner kernel models each unit's cost and every CTA of a persistent grid (one per SM) gets a
+//    cost-balanced contiguous range, which its two 8-warp halves consume from both ends (dynamic
+//    meeting point), so there is no wave tail and no idle half; row partials are fixed-point integers
+//    written to a (segment, half, row tile) slot: the result does not depend on the split.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -841,7 +843,6 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     a.Bpad = L.Bpad; a.n_rows = n_rows;
     a.n_row_tiles = L.n_row_tiles; a.S = L.S; a.F = L.F; a.n_rr = L.n_rr;
     a.P = golden_stride(L.S);
-    if (const char *dbg = getenv("ARVAE_DEBUG_STRIDE")) a.P = atoi(dbg) > 0 ? atoi(dbg) : a.P;  // experiments only
     int64_t G = (int64_t)sm_count() * tiles_ctas_per_sm(want_grad);
     if (G > L.G_max) G = L.G_max;
     if (G < 1) G = 1;
