@@ -441,6 +441,10 @@ def compute_kld_loss(z_dist, prior_dist, beta, c=0.0) -> torch.Tensor:
     :func:`reparametrize` produced ``prior_dist``, else computed by the head kernel now."""
     kld = getattr(prior_dist, "_arvae_kld_mean", None)
     if kld is None or getattr(prior_dist, "_arvae_kld_of", None) is not z_dist:
+        # not produced by our reparametrize: the closed form below is only valid against N(0, 1) -- the only prior
+        # the reference ever builds (imagevae/mnist_vae.py:82-85) -- so check it (one sync, off the usual path)
+        if not (bool((prior_dist.loc == 0).all()) and bool((prior_dist.scale == 1).all())):
+            raise RuntimeError("arvae_b200.compute_kld_loss: prior_dist must be the unit Normal(0, 1)")
         loc, scale = z_dist.loc, z_dist.scale
         _, kld = latent_head(loc, scale, torch.zeros_like(loc))
     return beta * (kld - c).abs()

@@ -153,7 +153,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     from arvae_b200 import synth
-    case = synth.make_case(WORKLOAD)
+    case = synth.make_case(WORKLOAD, args.batch or None)
     B, R = case["B"], len(case["reg_dims"])
     budget = 150.0 / max(1, args.steps + args.warmup)
     value, info = cpu_reference_sample(case, min(20.0, budget), steps=args.steps, warmup=args.warmup)

@@ -72,3 +72,17 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "arvae_oracle" not in text, f
+
+
+def test_ctypes_table_has_the_arity_of_every_prototype(lib):
+    """Guards against ABI drift: the number of parameters in each header prototype equals the number of
+    ctypes argtypes bound for it."""
+    from arvae_b200 import _lib
+    text = open(os.path.join(REPO, "include", "arvae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"ARVAE_API[^;(]*?\b(arvae_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
