@@ -178,6 +178,15 @@ def _normalize_dims(reg_dims: Sequence[int], Z: int) -> Tuple[int, ...]:
     return tuple(out)
 
 
+def _upcast_half(z: torch.Tensor):
+    """float16 / bfloat16 latents (autocast) are computed in float32 -- strictly more accurate than the reference's
+    half-precision op chain -- and the result is cast back to the input dtype, as the reference's would be.
+    float64 is NOT silently narrowed: it raises in _require_cuda_f32."""
+    if isinstance(z, torch.Tensor) and z.is_cuda and z.dtype in (torch.float16, torch.bfloat16):
+        return z.float(), z.dtype
+    return z, None
+
+
 def reg_loss_fused(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], gamma, factor=1.0,
                    label_cols: Optional[Sequence[int]] = None, algo: int = ALGO_AUTO) -> torch.Tensor:
     """All regularised dims in one launch: the value the trainers' loop accumulates
@@ -186,6 +195,9 @@ def reg_loss_fused(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int
     ``labels`` is the [B, A] attribute matrix; label column ``dim`` pairs with latent ``dim``
     unless ``label_cols`` says otherwise.  Returns a 0-d float32 tensor, differentiable w.r.t. ``z``.
     """
+    z, back = _upcast_half(z)
+    if back is not None:
+        return reg_loss_fused(z, labels, reg_dims, gamma, factor, label_cols, algo).to(back)
     _require_cuda_f32(z, "z")
     if z.dim() != 2:
         raise RuntimeError(f"arvae_b200: z must be [B, Z], got shape {tuple(z.shape)}")
@@ -206,6 +218,9 @@ def compute_reg_loss(z: torch.Tensor, labels: torch.Tensor, reg_dim: Union[int, 
     """
     if isinstance(reg_dim, (tuple, list)):
         return reg_loss_fused(z, labels, tuple(reg_dim), gamma, factor)
+    z, back = _upcast_half(z)
+    if back is not None:
+        return compute_reg_loss(z, labels, reg_dim, gamma, factor).to(back)
     _require_cuda_f32(z, "z")
     if z.dim() != 2:
         raise RuntimeError(f"arvae_b200: z must be [B, Z], got shape {tuple(z.shape)}")
@@ -218,6 +233,9 @@ def compute_reg_loss(z: torch.Tensor, labels: torch.Tensor, reg_dim: Union[int, 
 
 def reg_loss_sign(latent_code: torch.Tensor, attribute: torch.Tensor, factor=1.0) -> torch.Tensor:
     """Drop-in for ``Trainer.reg_loss_sign`` (utils/trainer.py:378-403): both arguments are [N]."""
+    latent_code, back = _upcast_half(latent_code)
+    if back is not None:
+        return reg_loss_sign(latent_code, attribute, factor).to(back)
     _require_cuda_f32(latent_code, "latent_code")
     x = latent_code.reshape(-1, 1)
     lab, lcols = _prepare_labels(attribute.reshape(-1), (0,), x.shape[0], x.device)

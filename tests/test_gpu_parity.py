@@ -494,3 +494,25 @@ def test_graph_captured_latent_head_matches_eager(ab):
     assert_loss_close(reg.item(), g["reg_loss"])
     assert_grad_close(loc.grad.cpu().numpy(), g["grad_loc"])
     assert_grad_close(scale.grad.cpu().numpy(), g["grad_scale"])
+
+
+def test_half_precision_latents_are_upcast_and_float64_is_refused(ab):
+    g = golden("reg_c1_mnist_b64")
+    labels = dev(g["labels"])
+    dims = tuple(int(d) for d in g["reg_dims"])
+    for dt in (torch.bfloat16, torch.float16):
+        z = dev(g["z"]).to(dt).requires_grad_(True)
+        loss = ab.reg_loss_fused(z, labels, dims, float(g["gamma"]), float(g["delta"]))
+        assert loss.dtype == dt
+        loss.backward()
+        assert z.grad.dtype == dt and torch.isfinite(z.grad.float()).all()
+        # equals the float32 op on the rounded latents, rounded back
+        z32 = z.detach().float().requires_grad_(True)
+        ref = ab.reg_loss_fused(z32, labels, dims, float(g["gamma"]), float(g["delta"]))
+        ref.backward()
+        assert torch.equal(loss.detach(), ref.detach().to(dt))
+        assert torch.equal(z.grad, z32.grad.to(dt))
+        one = ab.compute_reg_loss(z.detach(), labels[:, 1], 1, 10.0)
+        assert one.dtype == dt
+    with pytest.raises(RuntimeError, match="float32"):
+        ab.reg_loss_fused(dev(g["z"]).double(), labels, dims, 1.0, 1.0)
