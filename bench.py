@@ -39,6 +39,8 @@ MUFU_LANES_PER_CLK_SM = 16.0     # sm_100 MUFU issue rate; confirmed by bench_to
 # dense form) on the dense path; 1 (RCP only, E_j/(E_i+E_j) with E = 2^u precomputed per element) where
 # the attribute-sorted path's range guard holds.  Measured per run via arvae_b200.mufu_per_pair().
 ALGO_BYTES_PER_ROWCOL = 4        # float32 per latent / label / gradient element
+# (B, R, n_gpus, algo) -> dram__bytes_read.sum + dram__bytes_write.sum of one pair-kernel launch (ncu, profiles/)
+NCU_DRAM_BYTES_PER_LAUNCH = {(65536, 6, 1, 0): 5261056 + 0}
 
 
 def load_peaks():
@@ -373,9 +375,13 @@ def main():
     pairs_per_launch = pairs / world  # this rank's rows x all columns x R
     achieved = pairs_per_launch / (k_ms * 1e-3) / 1e9
     algo_bytes = (2 * B * R + n_local * R) * ALGO_BYTES_PER_ROWCOL  # columns in (u, a) + gradient columns out
+    # DRAM traffic of the pair kernel per launch, from the ncu --set full capture of this same command committed
+    # under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum); only known for the configuration profiled
+    traffic = NCU_DRAM_BYTES_PER_LAUNCH.get((B, R, world, int(args.algo)))
     roofline = {
         "bound": "mufu", "achieved": achieved, "peak": mufu_peak, "unit": "Gpairs/s", "frac": achieved / mufu_peak,
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": "profiles/r1_final_ncu_full_summary.csv (ncu --set full, reg_tiles_kernel<true>)" if traffic else None,
         "peak_source": f"{MUFU_LANES_PER_CLK_SM:.0f} MUFU lanes/clk/SM x {sm_count} SMs x {f_ghz:.3f} GHz (sm_max_mhz, "
                        f"MEASURED_PEAKS.json {peaks_src}) / {MUFU_PER_PAIR:.2f} MUFU per evaluated pair (this run's "
                        "algorithm; every one of the B^2 R ordered pairs is evaluated); "
