@@ -5,10 +5,14 @@
 // so keys are unique, ties come out ordered by original index, NaN sorts after +inf and padding
 // after NaN -- the order is a pure function of the inputs (deterministic).  B log^2 B work on
 // O(B R) data: noise next to the B^2 R pair sweep, so a simple shared-memory bitonic network is enough.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "reg_internal.cuh"
 
 namespace arvae {
+
+namespace cg = cooperative_groups;
 
 #ifndef ARVAE_SORT_CHUNK
 #define ARVAE_SORT_CHUNK 2048
@@ -198,6 +202,107 @@ bitonic_global_kernel(unsigned long long *__restrict__ keys, int64_t N, int64_t 
     for (int m = 0; m < E; ++m) base[i0 + (int64_t)m * jl] = v[m];
 }
 
+// The whole sort in ONE cooperative launch (grid-wide barriers instead of ~13 kernel boundaries) when every
+// (chunk, dim) CTA can be resident at once -- true for the C4 shape (32 chunks x 6 dims = 192 CTAs of 256 threads).
+// Same network, same device functions, same result as the multi-launch path below.
+template <int STEPS>
+__device__ __forceinline__ void coop_global_round(unsigned long long *__restrict__ base, int64_t N, int64_t k, int64_t j,
+                                                  int64_t t0, int64_t nthreads) {
+    constexpr int E = 1 << STEPS;
+    const int64_t jl = j >> (STEPS - 1);
+    for (int64_t t = t0; t < (N >> STEPS); t += nthreads) {
+        const int64_t i0 = ((t & ~(jl - 1)) << STEPS) | (t & (jl - 1));
+        const bool asc = ((i0 & k) == 0);
+        unsigned long long v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = base[i0 + (int64_t)m * jl];
+#pragma unroll
+        for (int st = STEPS - 1; st >= 0; --st)
+#pragma unroll
+            for (int m = 0; m < E; ++m)
+                if ((m & (1 << st)) == 0) cmpx(v[m], v[m | (1 << st)], asc);
+#pragma unroll
+        for (int m = 0; m < E; ++m) base[i0 + (int64_t)m * jl] = v[m];
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+bitonic_coop_kernel(unsigned long long *__restrict__ keys, int64_t N, const float *__restrict__ lab, int64_t lrs,
+                    int64_t lcs, RegDims dims, int64_t B) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned long long s[];
+    unsigned long long *dim_base = keys + (int64_t)blockIdx.y * N;
+    unsigned long long *base = dim_base + (int64_t)blockIdx.x * kSortChunk;
+    const int64_t g0 = (int64_t)blockIdx.x * kSortChunk;
+    const int n = (int)min((int64_t)kSortChunk, N);
+    for (int i = threadIdx.x; i < n; i += kSortThreads) {
+        const int64_t j = g0 + i;
+        unsigned long long k = ~0ull;  // padding sorts last
+        if (j < B) {
+            const float a = __ldg(lab + j * lrs + (int64_t)dims.lcol[blockIdx.y] * lcs);
+            k = ((unsigned long long)float_to_sortable(a) << 32) | (unsigned long long)(unsigned int)j;
+        }
+        s[i] = k;
+    }
+    __syncthreads();
+    smem_round_tail(s, n, g0, 2, min(256, n));
+    __syncthreads();
+    for (int64_t k = 512; k <= n; k <<= 1) {
+        smem_steps_down_to_256(s, n, g0, k, (int)(k >> 1));
+        smem_round_tail(s, n, g0, k, k);
+        __syncthreads();
+    }
+    const int64_t t0 = (int64_t)blockIdx.x * kSortThreads + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * kSortThreads;
+    for (int64_t k = 2 * (int64_t)kSortChunk; k <= N; k <<= 1) {
+        for (int i = threadIdx.x; i < n; i += kSortThreads) base[i] = s[i];
+        grid.sync();  // every chunk of this stage is in global memory
+        int64_t j = k >> 1;
+        while (j >= kSortChunk) {
+            int steps = 0;
+            for (int64_t jj = j; jj >= kSortChunk && steps < 3; jj >>= 1) ++steps;
+            if (steps == 3) coop_global_round<3>(dim_base, N, k, j, t0, nthreads);
+            else if (steps == 2) coop_global_round<2>(dim_base, N, k, j, t0, nthreads);
+            else coop_global_round<1>(dim_base, N, k, j, t0, nthreads);
+            j >>= steps;
+            grid.sync();
+        }
+        for (int i = threadIdx.x; i < n; i += kSortThreads) s[i] = base[i];
+        __syncthreads();
+        smem_steps_down_to_256(s, n, g0, k, n >> 1);
+        smem_round_tail(s, n, g0, k, k);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += kSortThreads) base[i] = s[i];
+}
+
+// Can the cooperative single-launch sort be used for this shape on this device, on this stream right now?
+static bool coop_sort_possible(int64_t chunks, int R, size_t smem, cudaStream_t st) {
+    static int cache[64] = {};  // per device: max co-resident CTAs of bitonic_coop_kernel, -1 = unsupported
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (cache[dev] == 0) {
+        int coop = 0, per_sm = 0, sms = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitonic_coop_kernel, kSortThreads,
+                                                                    kSortChunk * sizeof(unsigned long long)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            cache[dev] = -1;
+        } else {
+            cache[dev] = per_sm * sms > 0 ? per_sm * sms : -1;
+        }
+    }
+    if (cache[dev] < 0 || chunks * R > cache[dev]) return false;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return false;  // keep graph capture on the plain multi-launch path
+    }
+    (void)smem;
+    return true;
+}
+
 int64_t sort_padded_size(int64_t B) {
     int64_t n = 256;
     while (n < B) n <<= 1;
@@ -217,6 +322,16 @@ int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dim
     const int64_t chunks = N > kSortChunk ? N / kSortChunk : 1;
     const size_t smem = (size_t)(N < kSortChunk ? N : kSortChunk) * sizeof(unsigned long long);
     dim3 gl((unsigned)chunks, (unsigned)R);
+    if (chunks > 1 && coop_sort_possible(chunks, R, smem, st)) {
+        RegDims d = dims;
+        void *args[] = {(void *)&keys, (void *)&N, (void *)&lab, (void *)&lrs, (void *)&lcs, (void *)&d, (void *)&B};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)bitonic_coop_kernel, gl, dim3(kSortThreads), args, smem, st);
+        if (e == cudaSuccess) {
+            count_launch();
+            return 0;
+        }
+        (void)cudaGetLastError();  // e.g. co-residency not available right now: fall through to the plain path
+    }
     bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, 0, lab, lrs, lcs, dims, B);
     ARVAE_LAUNCH_CHECK("bitonic_local_kernel");
     for (int64_t k = 2 * (int64_t)kSortChunk; k <= N; k <<= 1) {
