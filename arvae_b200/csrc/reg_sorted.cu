@@ -561,7 +561,11 @@ reg_tiles_kernel(TilesArgs a) {
     // flush this half's partial sums of row tile cur_rr into its slot (segment of this CTA, half)
     auto flush = [&]() {
         if (cur_rr < 0) return;
-        const int64_t seg = c - owner_of_pos(a.prefix[cur_rr], T, a.G);
+        int64_t seg = c - owner_of_pos(a.prefix[cur_rr], T, a.G);
+        if (seg >= a.max_segs) {  // cannot happen within the modelled cost ratios; never write out of bounds
+            if (tid == 0) atomicExch(const_cast<int *>(a.flags) + ARVAE_MAX_REG_DIMS, 1);  // epilogue reports NaN
+            seg = a.max_segs - 1;
+        }
         const int64_t slot = (((seg * 2 + half) * a.n_rr) + cur_rr) * kTileRows;
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
@@ -705,7 +709,8 @@ reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int6
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            const double total = sh[0] - pad_per_row * (double)a.n_rows * (double)R;
+            double total = sh[0] - pad_per_row * (double)a.n_rows * (double)R;
+            if (a.flags[ARVAE_MAX_REG_DIMS]) total = __longlong_as_double(0x7ff8000000000000LL);  // slot overflow: NaN, not a wrong number
             *loss_out = total * lscale;
             if (loss_f32_out) *loss_f32_out = (float)(total * lscale);
         }
@@ -787,7 +792,7 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
     L.off_Es = take(sizeof(float) * (size_t)R * L.Bpad);
     L.off_perm = take(sizeof(int) * (size_t)R * L.Bpad);
     L.off_rowpos = take(sizeof(int) * (size_t)R * (n_rows > 0 ? n_rows : 1));
-    L.off_flags = take(sizeof(int) * ARVAE_MAX_REG_DIMS);
+    L.off_flags = take(sizeof(int) * (ARVAE_MAX_REG_DIMS + 1));  // [R] range-guard flags + one overflow flag
     L.off_blockcnt = take(sizeof(int) * (size_t)R * (size_t)ceil_div(L.Bpad, 256));
     L.off_cls8 = take(sizeof(unsigned int) * (size_t)L.F);
     L.off_cost8 = take(sizeof(unsigned short) * (size_t)L.F);
@@ -819,7 +824,7 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
 
     int rc = run_sort_keys(P.lab, P.lrs, P.lcs, P.dims, P.R, P.B, L.N, keys, st);
     if (rc) return rc;
-    ARVAE_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * ARVAE_MAX_REG_DIMS, st));
+    ARVAE_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * (ARVAE_MAX_REG_DIMS + 1), st));
     const double c = 2.0 * (double)P.factor * 1.4426950408889634074;  // 2 f log2(e)
     const float fsign = P.factor > 0.f ? 1.0f : (P.factor < 0.f ? -1.0f : 0.0f);
     const float cabs = P.factor != 0.f ? (float)fabs(c) : 1.0f;  // f == 0: xs == 0, any scale works

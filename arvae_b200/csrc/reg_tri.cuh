@@ -320,7 +320,11 @@ reg_tri_kernel(TilesArgs a) {
         __syncthreads();
         if (threadIdx.x < kStageSubs) swords[threadIdx.x] = 0u;
 
-        const int64_t seg = min((int64_t)(c - owner_of_pos(a.prefix[rr], T, a.G)), (int64_t)a.max_segs - 1);
+        int64_t seg = c - owner_of_pos(a.prefix[rr], T, a.G);
+        if (seg >= a.max_segs) {
+            if (threadIdx.x == 0) atomicExch(const_cast<int *>(a.flags) + ARVAE_MAX_REG_DIMS, 1);
+            seg = a.max_segs - 1;
+        }
         const int64_t slot = (seg * a.n_rr + rr) * kTileRows;
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
@@ -413,8 +417,8 @@ reg_tri_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, double
 
 __global__ void __launch_bounds__(256)
 reg_tri_finish_kernel(const acc_t *__restrict__ lossp, int64_t n_lossp, const double *__restrict__ eloss,
-                      int64_t n_eloss, double pad_total, double lscale, double *__restrict__ loss_out,
-                      float *__restrict__ loss_f32_out) {
+                      int64_t n_eloss, double pad_total, double lscale, const int *__restrict__ overflow_flag,
+                      double *__restrict__ loss_out, float *__restrict__ loss_f32_out) {
     __shared__ double sh[256];
     double t = 0.0;
     for (int64_t u = threadIdx.x; u < n_lossp; u += 256) t += (double)lossp[u] * kLossScale;
@@ -426,7 +430,8 @@ reg_tri_finish_kernel(const acc_t *__restrict__ lossp, int64_t n_lossp, const do
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const double total = (sh[0] - pad_total) * lscale;
+        double total = (sh[0] - pad_total) * lscale;
+        if (overflow_flag && *overflow_flag) total = __longlong_as_double(0x7ff8000000000000LL);
         *loss_out = total;
         if (loss_f32_out) *loss_f32_out = (float)total;
     }
@@ -497,7 +502,7 @@ static int run_reg_tri_tail(const RegProblem &P, const SortedLayout &L, TilesArg
                                                                P.row_loss_out, eloss);
     ARVAE_LAUNCH_CHECK("reg_tri_epilogue_kernel");
     reg_tri_finish_kernel<<<1, 256, 0, st>>>(a.lossp, a.G, eloss, n_eblocks, pad_per_row * (double)P.B * (double)P.R,
-                                             lscale, P.loss_out, P.loss_f32_out);
+                                             lscale, a.flags + ARVAE_MAX_REG_DIMS, P.loss_out, P.loss_f32_out);
     ARVAE_LAUNCH_CHECK("reg_tri_finish_kernel");
     return 0;
 }
