@@ -47,6 +47,9 @@ SIGNATURES = {
     "arvae_attr_argsort_workspace_bytes": (_sz, [_i64]),
     "arvae_attr_argsort_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "arvae_measure_attributes_i64": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "arvae_eval_metrics_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "arvae_eval_metrics_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp,
+                                              _vp, _vp, _sz, _vp]),
     "arvae_reg_sign_matrix_i8": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "arvae_launch_count": (_i64, [ctypes.c_int]),
     "arvae_profile_enable": (None, [ctypes.c_int]),

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libarvae_b200.so")
-SOURCES = ["api.cu", "reg_dense.cu", "reg_sorted.cu", "sort.cu", "latent_head.cu", "music_attrs.cu"]
+SOURCES = ["api.cu", "reg_dense.cu", "reg_sorted.cu", "sort.cu", "latent_head.cu", "music_attrs.cu", "eval_metrics.cu"]
 HEADERS = ["common.cuh", "reg_internal.cuh", os.path.join("..", "..", "include", "arvae_b200.h")]
 
 NVCC_FLAGS = [

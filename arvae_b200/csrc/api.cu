@@ -424,6 +424,36 @@ int arvae_measure_attributes_i64(const int64_t *measures_dev, int64_t B, int64_t
                                   rhy_weights_dev, out_dev, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t arvae_eval_metrics_workspace_bytes(int64_t B, int32_t Z, int32_t A) {
+    if (B < 1 || Z < 1 || A < 1 || Z > kEvalMaxCodes || A > kEvalMaxAttrs) return 0;
+    return eval_metrics_workspace_bytes(B, Z, A);
+}
+
+int arvae_eval_metrics_f32(const float *codes_dev, int64_t codes_row_stride, int64_t codes_col_stride,
+                           const float *attrs_dev, int64_t attrs_row_stride, int64_t attrs_col_stride, int64_t B,
+                           int32_t Z, int32_t A, double *rho_out_dev, double *pval_out_dev, double *corr_out_dev,
+                           double *sap_out_dev, double *scores_out_dev, void *workspace_dev, size_t workspace_bytes,
+                           void *stream) {
+    if (B < 1 || B > 0x7fffffffLL || Z < 1 || A < 1 || Z > kEvalMaxCodes || A > kEvalMaxAttrs) {
+        set_error("eval_metrics: need 1 <= B < 2^31, 1 <= Z <= %d, 1 <= A <= %d (got B=%lld Z=%d A=%d)", kEvalMaxCodes,
+                  kEvalMaxAttrs, (long long)B, (int)Z, (int)A);
+        return ARVAE_E_BADARG;
+    }
+    if (!codes_dev || !attrs_dev || !rho_out_dev || !pval_out_dev || !corr_out_dev || !sap_out_dev ||
+        !scores_out_dev || !workspace_dev) {
+        set_error("null pointer argument to eval_metrics");
+        return ARVAE_E_BADARG;
+    }
+    if (workspace_bytes < eval_metrics_workspace_bytes(B, Z, A)) {
+        set_error("workspace too small for eval_metrics");
+        return ARVAE_E_WORKSPACE;
+    }
+    return run_eval_metrics(codes_dev, codes_row_stride, codes_col_stride, attrs_dev, attrs_row_stride,
+                            attrs_col_stride, B, Z, A, rho_out_dev, pval_out_dev, corr_out_dev, sap_out_dev,
+                            scores_out_dev, reinterpret_cast<char *>(workspace_dev),
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
 int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
                              int8_t *out_dev, void *stream) {
     if (B < 0 || (B > 0 && (!labels_dev || !out_dev))) {

@@ -70,6 +70,13 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
 int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStream_t st);
 constexpr int64_t kSortedMinBatch = 8192;  // ARVAE_ALGO_AUTO switches to the sorted path from here
 
+// pairwise-rank evaluation metrics (eval_metrics.cu)
+constexpr int kEvalMaxCodes = 1024, kEvalMaxAttrs = 64;
+size_t eval_metrics_workspace_bytes(int64_t B, int Z, int A);
+int run_eval_metrics(const float *codes, int64_t crs, int64_t ccs, const float *attrs, int64_t ars, int64_t acs,
+                     int64_t B, int Z, int A, double *rho, double *pval, double *corr, double *sap, double *scores,
+                     char *ws, cudaStream_t st);
+
 // latent head (latent_head.cu)
 size_t latent_head_ws_bytes(int64_t B, int64_t Z);
 int run_latent_head_fwd(const float *loc, const float *scale, const float *eps, int64_t B,

@@ -196,6 +196,27 @@ ARVAE_API int arvae_measure_attributes_i64(const int64_t *measures_dev, int64_t 
                                            int64_t row_stride, const int32_t *lut_dev, int64_t V,
                                            const float *rhy_weights_dev, float *out_dev, void *stream);
 
+/*
+ * Pairwise-rank evaluation metrics of the reference (utils/evaluation.py): for latent codes [B, Z] and
+ * attributes [B, A] (float32, element strides), every (code i, attribute j) pair gets
+ *   rho_out_dev[i*A+j], pval_out_dev[i*A+j]  Spearman rho and its two-sided p-value, as scipy.stats.spearmanr
+ *                                            returns them at utils/evaluation.py:166 (average ranks for ties;
+ *                                            NaN for constant or NaN-holding columns and for B < 3);
+ *   corr_out_dev[i*A+j]                      _compute_correlation_matrix (:157-173): |rho| if p <= 0.05 else 0;
+ *   sap_out_dev[i*A+j]                       _compute_score_matrix (:194-214): cov^2/(var_mu var_y), ddof = 1,
+ *                                            0 where var_mu <= 1e-12 (IEEE NaN/inf where var_y = 0, as numpy);
+ *   scores_out_dev[0..1]                     { Corr_score (:146-155), SAP_score (:176-191, :217-219) }.
+ * All outputs are device doubles; all arithmetic after the argsort is float64 like the reference's.
+ * 1 <= Z <= 1024, 1 <= A <= 64, B >= 1.  workspace: arvae_eval_metrics_workspace_bytes(B, Z, A) bytes.
+ * Stream-ordered, no host sync; bitwise reproducible.
+ */
+ARVAE_API size_t arvae_eval_metrics_workspace_bytes(int64_t B, int32_t Z, int32_t A);
+ARVAE_API int arvae_eval_metrics_f32(const float *codes_dev, int64_t codes_row_stride, int64_t codes_col_stride,
+                                     const float *attrs_dev, int64_t attrs_row_stride, int64_t attrs_col_stride,
+                                     int64_t B, int32_t Z, int32_t A, double *rho_out_dev, double *pval_out_dev,
+                                     double *corr_out_dev, double *sap_out_dev, double *scores_out_dev,
+                                     void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* s[i*B+j] = sign(a_i - a_j) as int8, for parity tests at small B (same compare the kernels use). */
 ARVAE_API int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,
                              int8_t *out_dev, void *stream);
