@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import re
-from typing import Callable, Dict, Mapping, Optional, Sequence
+from typing import Callable, Mapping, Optional, Sequence
 
 import torch
 

@@ -30,7 +30,6 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 WORKLOAD = "c4_mnist_b65536"

@@ -1,5 +1,5 @@
-import sys, os, torch
-sys.path.insert(0, "/root/repo")
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import arvae_b200
 for B in (8192, 65536, 262144):
     a = torch.randn(B, device="cuda")
