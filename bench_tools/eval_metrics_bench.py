@@ -61,7 +61,7 @@ cpu_ms = (time.perf_counter() - t) * 1e3
 emit({"section": "timing", "N": int(mus_h.shape[0]), "Z": int(mus_h.shape[1]), "A": int(ys_h.shape[1]),
       "gpu_ms_device_inputs": gpu_ms, "e2e_ms_numpy_inputs": e2e_ms, "launches_per_call": launches,
       "cpu_oracle_numpy_ms": cpu_ms, "algorithmic_bytes": int(mus_h.nbytes + ys_h.nbytes),
-      "note": "reference itself: Z*A scipy.stats.spearmanr + np.cov calls, ~1.1 s here (see tests/golden/make_golden_eval.py)"})
+      "note": "reference itself: Z*A scipy.stats.spearmanr + np.cov calls, ~0.87 s here (see tests/golden/make_golden_eval.py)"})
 out_dir = os.path.join(ROOT, "gpurun_out")
 if os.path.isdir(out_dir):
     with open(os.path.join(out_dir, "eval_metrics_bench.json"), "w") as f:
