@@ -31,7 +31,7 @@ SIGNATURES = {
     "arvae_reg_loss_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "arvae_reg_loss_workspace_bytes_algo": (_sz, [_i64, _i64, _i32, _i32]),
     "arvae_reg_loss_fwdbwd_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _c_i32p, _c_i32p, _i32,
-                                                 _i64, _i64, _i64, _f, _f, _i32, _vp, _vp, _vp, _vp, _vp,
+                                                 _i64, _i64, _i64, _f, _f, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                                  _sz, _vp]),
     "arvae_reg_loss_path_flags": (ctypes.c_int, [_i64, _i64, _i32, _i32, _vp, _c_i32p, _vp]),
     "arvae_reg_loss_scatter_bwd_f32": (ctypes.c_int, [_vp, _vp, _c_i32p, _i32, _i64, _i64, _vp, _i64, _vp]),
@@ -51,6 +51,18 @@ SIGNATURES = {
     "arvae_eval_metrics_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp,
                                               _vp, _vp, _sz, _vp]),
     "arvae_reg_sign_matrix_i8": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "arvae_shard_comm_bytes": (_sz, [_i64, _i32, _i32]),
+    "arvae_shard_create": (ctypes.c_int, [_i32, _i32, _i64, _i32, ctypes.POINTER(_vp)]),
+    "arvae_shard_ipc_handle": (ctypes.c_int, [_vp, _vp]),
+    "arvae_shard_open_peers": (ctypes.c_int, [_vp, _vp]),
+    "arvae_shard_set_peer": (ctypes.c_int, [_vp, _i32, _vp]),
+    "arvae_shard_comm_ptr": (_vp, [_vp]),
+    "arvae_shard_reg_loss_f32": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _c_i32p, _c_i32p, _i32,
+                                                ctypes.POINTER(_i64), _f, _f, _vp, _vp, _vp, _i32, _vp]),
+    "arvae_shard_reg_loss_host_f32": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _c_i32p, _c_i32p, _i32,
+                                                     ctypes.POINTER(_i64), _f, _f, _vp, _vp, _vp]),
+    "arvae_shard_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_uint64), _vp]),
+    "arvae_shard_destroy": (ctypes.c_int, [_vp]),
     "arvae_launch_count": (_i64, [ctypes.c_int]),
     "arvae_profile_enable": (None, [ctypes.c_int]),
     "arvae_profile_pair_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
@@ -72,7 +84,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        if lib.arvae_version() != 100:
+        if lib.arvae_version() != 200:
             raise RuntimeError("arvae_b200: libarvae_b200.so version mismatch; rebuild")
         _lib = lib
     return _lib
@@ -85,6 +97,10 @@ def last_error() -> str:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"arvae_b200: {what} failed (rc={rc}): {last_error()}")
+
+
+def i64_array(values):
+    return (ctypes.c_int64 * max(len(values), 1))(*[int(v) for v in values])
 
 
 def i32_array(values):

@@ -171,7 +171,7 @@ int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t 
                               const int32_t *label_cols_host, int32_t R, int64_t row_begin,
                               int64_t row_end, int64_t B_total, float gamma, float factor,
                               int32_t algo, double *loss_out_dev, float *loss_f32_out_dev,
-                              float *grad_cols_out_dev, double *row_loss_out_dev,
+                              float *grad_cols_out_dev, double *row_loss_out_dev, int32_t *row_sign_out_dev,
                               void *workspace_dev, size_t workspace_bytes, void *stream) {
     RegProblem P;
     int rc = fill_dims(P.dims, reg_dims_host, label_cols_host, R);
@@ -194,6 +194,7 @@ int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t 
     P.R = R; P.B = B_total; P.row_begin = row_begin; P.row_end = row_end;
     P.gamma = gamma; P.factor = factor;
     P.loss_out = loss_out_dev; P.loss_f32_out = loss_f32_out_dev; P.grad_cols_out = grad_cols_out_dev; P.row_loss_out = row_loss_out_dev;
+    P.row_sign_out = row_sign_out_dev;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     const bool sorted = algo == ARVAE_ALGO_SORTED || algo == ARVAE_ALGO_TRIANGLE ||
@@ -229,9 +230,12 @@ int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_
     }
     const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count(), algo == ARVAE_ALGO_TRIANGLE);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    ARVAE_CUDA_TRY(cudaMemcpyAsync(flags_out_host, reinterpret_cast<const char *>(workspace_dev) + LS.off_flags,
-                                   sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st));
+    int32_t tmp[3 * ARVAE_MAX_REG_DIMS + 1];
+    ARVAE_CUDA_TRY(cudaMemcpyAsync(tmp, reinterpret_cast<const char *>(workspace_dev) + LS.off_flags,
+                                   sizeof(tmp), cudaMemcpyDeviceToHost, st));
     ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
+    // whole-dim two-MUFU flag (triangle mode): report "no inliers"; else the inlier count of the segmented order
+    for (int r = 0; r < R; ++r) flags_out_host[r] = tmp[r] ? 0 : tmp[2 * ARVAE_MAX_REG_DIMS + 1 + r];
     return 0;
 }
 
@@ -329,28 +333,28 @@ int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z, const flo
     const size_t lb = sizeof(float) * (size_t)(B > 0 ? B : 1) * A;
     const size_t gb = sizeof(float) * (size_t)(B > 0 ? B : 1) * (R > 0 ? R : 1);
     const size_t wb = arvae_reg_loss_workspace_bytes_algo(B, B, R, algo);
-    if (C.z_bytes < zb) {
-        cudaFree(C.z); cudaFree(C.gz);
-        ARVAE_CUDA_TRY(cudaMalloc(&C.z, zb));
-        ARVAE_CUDA_TRY(cudaMalloc(&C.gz, zb));
-        C.z_bytes = zb;
+    // grow-only buffers; a failed allocation leaves the cache empty (no freed pointer or stale size survives)
+    auto grow = [&](void **ptr, size_t &have, size_t need) -> cudaError_t {
+        if (have >= need && *ptr) return cudaSuccess;
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        have = 0;
+        cudaError_t e = cudaMalloc(ptr, need);
+        if (e == cudaSuccess) have = need;
+        else *ptr = nullptr;
+        return e;
+    };
+    size_t gz_bytes = C.gz ? C.z_bytes : 0;
+    cudaError_t ge = grow(reinterpret_cast<void **>(&C.gz), gz_bytes, zb);
+    if (ge == cudaSuccess) ge = grow(reinterpret_cast<void **>(&C.z), C.z_bytes, zb);
+    if (ge == cudaSuccess) ge = grow(reinterpret_cast<void **>(&C.lab), C.lab_bytes, lb);
+    if (ge == cudaSuccess) ge = grow(reinterpret_cast<void **>(&C.gc), C.gc_bytes, gb);
+    if (ge == cudaSuccess) ge = grow(reinterpret_cast<void **>(&C.ws), C.ws_bytes, wb);
+    if (ge == cudaSuccess && !C.loss) ge = cudaMalloc(&C.loss, sizeof(double));
+    if (ge != cudaSuccess) {
+        C.release();
+        return fail_cuda(ge, "cudaMalloc (host-buffer cache)");
     }
-    if (C.lab_bytes < lb) {
-        cudaFree(C.lab);
-        ARVAE_CUDA_TRY(cudaMalloc(&C.lab, lb));
-        C.lab_bytes = lb;
-    }
-    if (C.gc_bytes < gb) {
-        cudaFree(C.gc);
-        ARVAE_CUDA_TRY(cudaMalloc(&C.gc, gb));
-        C.gc_bytes = gb;
-    }
-    if (C.ws_bytes < wb) {
-        cudaFree(C.ws);
-        ARVAE_CUDA_TRY(cudaMalloc(&C.ws, wb));
-        C.ws_bytes = wb;
-    }
-    if (!C.loss) ARVAE_CUDA_TRY(cudaMalloc(&C.loss, sizeof(double)));
 
     if (B > 0) {
         ARVAE_CUDA_TRY(cudaMemcpyAsync(C.z, z_host, sizeof(float) * (size_t)B * Z, cudaMemcpyHostToDevice, st));
@@ -358,7 +362,7 @@ int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z, const flo
     }
     rc = arvae_reg_loss_fwdbwd_f32(C.z, Z, 1, C.lab, A, 1, reg_dims_host, label_cols_host, R, 0, B, B,
                                    gamma, factor, algo, C.loss, nullptr, grad_z_out_host ? C.gc : nullptr,
-                                   nullptr, C.ws, C.ws_bytes, stream);
+                                   nullptr, nullptr, C.ws, C.ws_bytes, stream);
     if (rc) return rc;
     if (grad_z_out_host && B > 0) {
         rc = arvae_reg_loss_scatter_bwd_f32(C.gc, nullptr, reg_dims_host, R, B, Z, C.gz, Z, stream);
@@ -452,6 +456,215 @@ int arvae_eval_metrics_f32(const float *codes_dev, int64_t codes_row_stride, int
                             attrs_col_stride, B, Z, A, rho_out_dev, pval_out_dev, corr_out_dev, sap_out_dev,
                             scores_out_dev, reinterpret_cast<char *>(workspace_dev),
                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+
+// ---- sharded step over NVLink peer memory (reg_shard.cuh) --------------------------------------------------
+static ShardCtx *as_ctx(void *ctx) { return reinterpret_cast<ShardCtx *>(ctx); }
+
+size_t arvae_shard_comm_bytes(int64_t n_cap, int32_t R_cap, int32_t world) {
+    if (n_cap < 1 || R_cap < 1 || R_cap > ARVAE_MAX_REG_DIMS || world < 1 || world > kMaxShardRanks) return 0;
+    return shard_comm_bytes(n_cap, R_cap, world, nullptr);
+}
+
+int arvae_shard_create(int32_t rank, int32_t world, int64_t n_cap, int32_t R_cap, void **ctx_out) {
+    if (!ctx_out || world < 1 || world > kMaxShardRanks || rank < 0 || rank >= world || n_cap < 1 || R_cap < 1 ||
+        R_cap > ARVAE_MAX_REG_DIMS || (int64_t)world * n_cap > (int64_t)kKeyIdxMask) {
+        set_error("bad argument to shard_create (world <= %d, R_cap <= %d)", kMaxShardRanks, ARVAE_MAX_REG_DIMS);
+        return ARVAE_E_BADARG;
+    }
+    ShardCtx *C = new ShardCtx();
+    C->G = world; C->g = rank; C->R_cap = R_cap; C->n_cap = n_cap;
+    cudaError_t e = cudaGetDevice(&C->device);
+    if (e == cudaSuccess) {
+        C->comm_bytes = shard_comm_bytes(n_cap, R_cap, world, C);
+        C->ws_bytes = shard_ws_bytes(n_cap, R_cap, world, &C->off_mypos);
+        e = cudaMalloc(&C->comm, C->comm_bytes);
+    }
+    if (e == cudaSuccess) e = cudaMemset(C->comm, 0, C->comm_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&C->ws, C->ws_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(C->comm);
+        cudaFree(C->ws);
+        delete C;
+        return fail_cuda(e, "shard_create");
+    }
+    C->peer[rank] = C->comm;
+    *ctx_out = C;
+    return 0;
+}
+
+int arvae_shard_ipc_handle(void *ctx, void *handle_out) {
+    if (!ctx || !handle_out) {
+        set_error("null argument to shard_ipc_handle");
+        return ARVAE_E_BADARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == ARVAE_SHARD_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    ARVAE_CUDA_TRY(cudaIpcGetMemHandle(&h, as_ctx(ctx)->comm));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int arvae_shard_open_peers(void *ctx, const void *handles) {
+    if (!ctx || !handles) {
+        set_error("null argument to shard_open_peers");
+        return ARVAE_E_BADARG;
+    }
+    ShardCtx *C = as_ctx(ctx);
+    for (int h = 0; h < C->G; ++h) {
+        if (h == C->g || C->peer[h]) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, reinterpret_cast<const char *>(handles) + (size_t)h * ARVAE_SHARD_HANDLE_BYTES, sizeof(hd));
+        void *p = nullptr;
+        ARVAE_CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        C->peer[h] = reinterpret_cast<char *>(p);
+        C->opened[h] = true;
+    }
+    return 0;
+}
+
+int arvae_shard_set_peer(void *ctx, int32_t rank, void *comm_dev) {
+    ShardCtx *C = as_ctx(ctx);
+    if (!C || rank < 0 || rank >= C->G || !comm_dev) {
+        set_error("bad argument to shard_set_peer");
+        return ARVAE_E_BADARG;
+    }
+    C->peer[rank] = reinterpret_cast<char *>(comm_dev);
+    return 0;
+}
+
+void *arvae_shard_comm_ptr(void *ctx) { return ctx ? as_ctx(ctx)->comm : nullptr; }
+
+static int shard_fill_step(ShardCtx *C, ShardStep &S, const int32_t *reg_dims_host, const int32_t *label_cols_host,
+                           int32_t R, const int64_t *n_all_host) {
+    if (!C || !n_all_host) {
+        set_error("null argument to the shard step");
+        return ARVAE_E_BADARG;
+    }
+    for (int h = 0; h < C->G; ++h)
+        if (!C->peer[h]) {
+            set_error("shard step: peer %d is not mapped (call arvae_shard_open_peers / arvae_shard_set_peer first)", h);
+            return ARVAE_E_BADARG;
+        }
+    int rc = fill_dims(S.dims, reg_dims_host, label_cols_host, R);
+    if (rc) return rc;
+    S.R = R;
+    for (int h = 0; h < kMaxShardRanks; ++h) S.n_all[h] = h < C->G ? n_all_host[h] : 0;
+    return 0;
+}
+
+int arvae_shard_reg_loss_f32(void *ctx, const float *z_local_dev, int64_t z_row_stride, int64_t z_col_stride,
+                             const float *labels_local_dev, int64_t lab_row_stride, int64_t lab_col_stride,
+                             const int32_t *reg_dims_host, const int32_t *label_cols_host, int32_t R,
+                             const int64_t *n_all_host, float gamma, float factor, double *loss_out_dev,
+                             float *loss_f32_out_dev, float *grad_cols_out_dev, int32_t phases, void *stream) {
+    ShardCtx *C = as_ctx(ctx);
+    ShardStep S;
+    int rc = shard_fill_step(C, S, reg_dims_host, label_cols_host, R, n_all_host);
+    if (rc) return rc;
+    if (!loss_out_dev || (S.n_all[C->g] > 0 && (!z_local_dev || !labels_local_dev))) {
+        set_error("null pointer argument to shard_reg_loss");
+        return ARVAE_E_BADARG;
+    }
+    S.z = z_local_dev; S.zrs = z_row_stride; S.zcs = z_col_stride;
+    S.lab = labels_local_dev; S.lrs = lab_row_stride; S.lcs = lab_col_stride;
+    S.gamma = gamma; S.factor = factor;
+    S.loss_out = loss_out_dev; S.loss_f32_out = loss_f32_out_dev; S.grad_cols_out = grad_cols_out_dev;
+    S.phases = phases;
+    return run_shard_step(*C, S, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int arvae_shard_reg_loss_host_f32(void *ctx, const float *z_local_host, int64_t Z, const float *labels_local_host,
+                                  int64_t A, const int32_t *reg_dims_host, const int32_t *label_cols_host, int32_t R,
+                                  const int64_t *n_all_host, float gamma, float factor, float *loss_out_host,
+                                  float *grad_z_out_host, void *stream) {
+    ShardCtx *C = as_ctx(ctx);
+    ShardStep S;
+    int rc = shard_fill_step(C, S, reg_dims_host, label_cols_host, R, n_all_host);
+    if (rc) return rc;
+    const int64_t n = S.n_all[C->g];
+    if (Z <= 0 || A <= 0 || !loss_out_host || (n > 0 && (!z_local_host || !labels_local_host))) {
+        set_error("bad argument to shard_reg_loss_host");
+        return ARVAE_E_BADARG;
+    }
+    for (int r = 0; r < R; ++r)
+        if (S.dims.zcol[r] >= Z || S.dims.lcol[r] >= A) {
+            set_error("column index out of range at r=%d", r);
+            return ARVAE_E_BADARG;
+        }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t zb = sizeof(float) * (size_t)C->n_cap * Z, lb = sizeof(float) * (size_t)C->n_cap * A,
+                 gb = sizeof(float) * (size_t)C->n_cap * C->R_cap;
+    if (C->h_z_bytes < zb) {
+        cudaFree(C->h_z); cudaFree(C->h_gz);
+        C->h_z = C->h_gz = nullptr; C->h_z_bytes = 0;
+        ARVAE_CUDA_TRY(cudaMalloc(&C->h_z, zb));
+        ARVAE_CUDA_TRY(cudaMalloc(&C->h_gz, zb));
+        C->h_z_bytes = zb;
+    }
+    if (C->h_lab_bytes < lb) {
+        cudaFree(C->h_lab);
+        C->h_lab = nullptr; C->h_lab_bytes = 0;
+        ARVAE_CUDA_TRY(cudaMalloc(&C->h_lab, lb));
+        C->h_lab_bytes = lb;
+    }
+    if (C->h_gc_bytes < gb) {
+        cudaFree(C->h_gc);
+        C->h_gc = nullptr; C->h_gc_bytes = 0;
+        ARVAE_CUDA_TRY(cudaMalloc(&C->h_gc, gb));
+        C->h_gc_bytes = gb;
+    }
+    if (!C->h_loss) ARVAE_CUDA_TRY(cudaMalloc(&C->h_loss, sizeof(double)));
+    if (n > 0) {
+        ARVAE_CUDA_TRY(cudaMemcpyAsync(C->h_z, z_local_host, sizeof(float) * (size_t)n * Z, cudaMemcpyHostToDevice, st));
+        ARVAE_CUDA_TRY(cudaMemcpyAsync(C->h_lab, labels_local_host, sizeof(float) * (size_t)n * A, cudaMemcpyHostToDevice, st));
+    }
+    S.z = C->h_z; S.zrs = Z; S.zcs = 1;
+    S.lab = C->h_lab; S.lrs = A; S.lcs = 1;
+    S.gamma = gamma; S.factor = factor;
+    S.loss_out = C->h_loss; S.loss_f32_out = nullptr; S.grad_cols_out = grad_z_out_host ? C->h_gc : nullptr;
+    S.phases = 0;
+    rc = run_shard_step(*C, S, st);
+    if (rc) return rc;
+    if (grad_z_out_host && n > 0) {
+        rc = run_scatter_bwd(C->h_gc, nullptr, S.dims, R, n, Z, C->h_gz, Z, st);
+        if (rc) return rc;
+        ARVAE_CUDA_TRY(cudaMemcpyAsync(grad_z_out_host, C->h_gz, sizeof(float) * (size_t)n * Z, cudaMemcpyDeviceToHost, st));
+    }
+    double loss = 0.0;
+    ARVAE_CUDA_TRY(cudaMemcpyAsync(&loss, C->h_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
+    *loss_out_host = (float)loss;
+    return 0;
+}
+
+int arvae_shard_status(void *ctx, int32_t *status_out, uint64_t *epoch_out, void *stream) {
+    ShardCtx *C = as_ctx(ctx);
+    if (!C) {
+        set_error("null context");
+        return ARVAE_E_BADARG;
+    }
+    ShardHeader h;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ARVAE_CUDA_TRY(cudaMemcpyAsync(&h, C->comm, sizeof(h), cudaMemcpyDeviceToHost, st));
+    ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
+    if (status_out) *status_out = h.status;
+    if (epoch_out) *epoch_out = h.epoch;
+    return 0;
+}
+
+int arvae_shard_destroy(void *ctx) {
+    ShardCtx *C = as_ctx(ctx);
+    if (!C) return 0;
+    for (int h = 0; h < C->G; ++h)
+        if (C->opened[h]) cudaIpcCloseMemHandle(C->peer[h]);
+    cudaFree(C->comm); cudaFree(C->ws);
+    cudaFree(C->h_z); cudaFree(C->h_gz); cudaFree(C->h_lab); cudaFree(C->h_gc); cudaFree(C->h_loss);
+    (void)cudaGetLastError();
+    delete C;
+    return 0;
 }
 
 int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stride, int64_t B,

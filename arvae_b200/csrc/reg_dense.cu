@@ -50,9 +50,9 @@ pack_columns_kernel(const float *__restrict__ z, int64_t zrs, int64_t zcs,
 //   q = -s * 2^127 + d * 2^60 ;  sgn = clamp(q, -1, 1)
 // is exact whenever |d| >= 2^-60 or d == 0 (d * 2^60 only outweighs 2^127 when tanh is saturated
 // and the factor is 0 anyway).
-template <bool GRAD>
+template <bool GRAD, bool SIGNS = false>
 __device__ __forceinline__ void pair_general(float xi, float ai, float xj, float aj, float cabs,
-                                             float &lacc, float &gacc) {
+                                             float &lacc, float &gacc, float *kacc = nullptr) {
     const float d = xi - xj;
     const float e = ex2_approx(d * cabs);
     const float r = rcp_approx(e + 1.0f);
@@ -61,6 +61,7 @@ __device__ __forceinline__ void pair_general(float xi, float ai, float xj, float
     const float k = (1.0f - gt) + lt;  // 1 - s  in {0,1,2}
     const float v = fmaf(-2.0f, r, k);
     lacc += fabsf(v);
+    if (SIGNS) *kacc += k;  // small integers: exact
     if (GRAD) {
         const float w4 = fmaf(-r, r, r);
         const float q = fmaf(k - 1.0f, 1.7014118e38f, d * 1.1529215e18f);
@@ -69,12 +70,12 @@ __device__ __forceinline__ void pair_general(float xi, float ai, float xj, float
     }
 }
 
-template <int RI, bool GRAD>
+template <int RI, bool GRAD, bool SIGNS>
 __global__ void __launch_bounds__(kDenseThreads)
 reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, float cabs, int64_t Bpad,
                  int64_t row_begin, int64_t row_end, int64_t rows_pad, int64_t chunk_cols,
                  double *__restrict__ pgrad, double *__restrict__ prow,
-                 double *__restrict__ lossp) {
+                 double *__restrict__ lossp, int *__restrict__ psign) {
     __shared__ __align__(16) float su[kDenseTileCols];
     __shared__ __align__(16) float sa[kDenseTileCols];
     __shared__ double sred[kDenseThreads / 32];
@@ -89,6 +90,7 @@ reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, float
     float ui[RI], ai[RI];
     bool valid[RI];
     double dl[RI], dg[RI];
+    int ds[RI];  // sum_j sign(a_i - a_j) from the very compares the loss uses (parity instrumentation)
 #pragma unroll
     for (int k = 0; k < RI; ++k) {
         const int64_t row = row_begin + rb0 + threadIdx.x + (int64_t)k * kDenseThreads;
@@ -97,6 +99,7 @@ reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, float
         ai[k] = valid[k] ? Ar[row] : 0.0f;
         dl[k] = 0.0;
         dg[k] = 0.0;
+        ds[k] = 0;
     }
 
     const int64_t c0 = (int64_t)chunk * chunk_cols;
@@ -110,25 +113,26 @@ reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, float
         }
         __syncthreads();
         for (int s0 = 0; s0 < n; s0 += kSubCols) {
-            float lacc[RI], gacc[RI];
+            float lacc[RI], gacc[RI], kacc[RI];
 #pragma unroll
-            for (int k = 0; k < RI; ++k) lacc[k] = gacc[k] = 0.0f;
+            for (int k = 0; k < RI; ++k) lacc[k] = gacc[k] = kacc[k] = 0.0f;
 #pragma unroll 2
             for (int q = 0; q < kSubCols; q += 4) {
                 const float4 uj = *reinterpret_cast<const float4 *>(su + s0 + q);
                 const float4 aj = *reinterpret_cast<const float4 *>(sa + s0 + q);
 #pragma unroll
                 for (int k = 0; k < RI; ++k) {
-                    pair_general<GRAD>(ui[k], ai[k], uj.x, aj.x, cabs, lacc[k], gacc[k]);
-                    pair_general<GRAD>(ui[k], ai[k], uj.y, aj.y, cabs, lacc[k], gacc[k]);
-                    pair_general<GRAD>(ui[k], ai[k], uj.z, aj.z, cabs, lacc[k], gacc[k]);
-                    pair_general<GRAD>(ui[k], ai[k], uj.w, aj.w, cabs, lacc[k], gacc[k]);
+                    pair_general<GRAD, SIGNS>(ui[k], ai[k], uj.x, aj.x, cabs, lacc[k], gacc[k], &kacc[k]);
+                    pair_general<GRAD, SIGNS>(ui[k], ai[k], uj.y, aj.y, cabs, lacc[k], gacc[k], &kacc[k]);
+                    pair_general<GRAD, SIGNS>(ui[k], ai[k], uj.z, aj.z, cabs, lacc[k], gacc[k], &kacc[k]);
+                    pair_general<GRAD, SIGNS>(ui[k], ai[k], uj.w, aj.w, cabs, lacc[k], gacc[k], &kacc[k]);
                 }
             }
 #pragma unroll
             for (int k = 0; k < RI; ++k) {
                 dl[k] += (double)lacc[k];
                 dg[k] += (double)gacc[k];
+                if (SIGNS) ds[k] += kSubCols - (int)kacc[k];  // sum s = n - sum (1 - s); padded columns have s = 0
             }
         }
     }
@@ -143,6 +147,7 @@ reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, float
         lsum += dl[k];
         if (GRAD) pgrad[o] = valid[k] ? dg[k] : 0.0;
         if (prow) prow[o] = dl[k];
+        if (SIGNS) psign[o] = valid[k] ? ds[k] : 0;
     }
     lsum = warp_sum(lsum);
     if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = lsum;
@@ -164,7 +169,7 @@ reg_epilogue_kernel(const double *__restrict__ pgrad, const double *__restrict__
                     int64_t rows_pad, int64_t n_units, double gscale, double lscale,
                     double pad_per_row, float *__restrict__ grad_cols,
                     double *__restrict__ row_loss, double *__restrict__ loss_out,
-                    float *__restrict__ loss_f32_out) {
+                    float *__restrict__ loss_f32_out, const int *__restrict__ psign, int *__restrict__ row_sign) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n_rows * R
     if (idx < n_rows * R) {
         const int64_t row = idx / R;
@@ -178,6 +183,11 @@ reg_epilogue_kernel(const double *__restrict__ pgrad, const double *__restrict__
             double l = 0.0;
             for (int c = 0; c < n_chunks; ++c) l += prow[((int64_t)c * R + r) * rows_pad + row];
             row_loss[idx] = l - pad_per_row;
+        }
+        if (row_sign) {
+            int t = 0;
+            for (int c = 0; c < n_chunks; ++c) t += psign[((int64_t)c * R + r) * rows_pad + row];
+            row_sign[idx] = t;
         }
     }
     if (blockIdx.x == 0) {
@@ -274,6 +284,7 @@ DenseLayout dense_layout(int64_t B_total, int64_t n_rows, int R, int sm_count) {
     L.off_pgrad = take(sizeof(double) * (size_t)L.n_chunks * R * L.rows_pad);
     L.off_prow = take(sizeof(double) * (size_t)L.n_chunks * R * L.rows_pad);
     L.off_lossp = take(sizeof(double) * (size_t)(L.n_units > 0 ? L.n_units : 1));
+    L.off_psign = take(sizeof(int) * (size_t)L.n_chunks * R * L.rows_pad);
     L.bytes = off;
     return L;
 }
@@ -281,14 +292,17 @@ DenseLayout dense_layout(int64_t B_total, int64_t n_rows, int R, int sm_count) {
 template <int RI>
 static void launch_dense(const DenseLayout &L, int R, bool want_grad, const float *U,
                          const float *A, float cabs, int64_t row_begin, int64_t row_end, double *pgrad,
-                         double *prow, double *lossp, cudaStream_t st) {
+                         double *prow, double *lossp, int *psign, cudaStream_t st) {
     dim3 grid((unsigned)L.n_row_blocks, (unsigned)L.n_chunks, (unsigned)R);
-    if (want_grad)
-        reg_dense_kernel<RI, true><<<grid, kDenseThreads, 0, st>>>(
-            U, A, cabs, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp);
+    if (psign)
+        reg_dense_kernel<RI, true, true><<<grid, kDenseThreads, 0, st>>>(
+            U, A, cabs, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp, psign);
+    else if (want_grad)
+        reg_dense_kernel<RI, true, false><<<grid, kDenseThreads, 0, st>>>(
+            U, A, cabs, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp, nullptr);
     else
-        reg_dense_kernel<RI, false><<<grid, kDenseThreads, 0, st>>>(
-            U, A, cabs, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp);
+        reg_dense_kernel<RI, false, false><<<grid, kDenseThreads, 0, st>>>(
+            U, A, cabs, L.Bpad, row_begin, row_end, L.rows_pad, L.chunk_cols, pgrad, prow, lossp, nullptr);
 }
 
 int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStream_t st) {
@@ -299,6 +313,11 @@ int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStrea
     double *lossp = reinterpret_cast<double *>(ws + L.off_lossp);
     const int64_t n_rows = P.row_end - P.row_begin;
     const bool want_grad = P.grad_cols_out != nullptr;
+    int *psign = P.row_sign_out ? reinterpret_cast<int *>(ws + L.off_psign) : nullptr;
+    if (psign && !want_grad) {
+        set_error("row sign sums need the gradient pass");
+        return ARVAE_E_BADARG;
+    }
 
     const double c = 2.0 * (double)P.factor * 1.4426950408889634074;  // 2 f log2(e)
     const float fsign = P.factor > 0.f ? 1.0f : (P.factor < 0.f ? -1.0f : 0.0f);
@@ -310,9 +329,9 @@ int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStrea
     if (L.n_units > 0) {
         profile_begin(st);
         if (L.RI == 4)
-            launch_dense<4>(L, P.R, want_grad, U, A, cabs, P.row_begin, P.row_end, pgrad, prow, lossp, st);
+            launch_dense<4>(L, P.R, want_grad, U, A, cabs, P.row_begin, P.row_end, pgrad, prow, lossp, psign, st);
         else
-            launch_dense<1>(L, P.R, want_grad, U, A, cabs, P.row_begin, P.row_end, pgrad, prow, lossp, st);
+            launch_dense<1>(L, P.R, want_grad, U, A, cabs, P.row_begin, P.row_end, pgrad, prow, lossp, psign, st);
         profile_end(st);
         ARVAE_LAUNCH_CHECK("reg_dense_kernel");
     }
@@ -325,7 +344,7 @@ int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStrea
     const int64_t work = n_rows * P.R;
     reg_epilogue_kernel<<<(unsigned)(work > 0 ? ceil_div(work, 256) : 1), 256, 0, st>>>(
         pgrad, prow, lossp, L.n_chunks, P.R, n_rows, L.rows_pad, L.n_units, gscale, lscale,
-        pad_per_row, P.grad_cols_out, P.row_loss_out, P.loss_out, P.loss_f32_out);
+        pad_per_row, P.grad_cols_out, P.row_loss_out, P.loss_out, P.loss_f32_out, psign, P.row_sign_out);
     ARVAE_LAUNCH_CHECK("reg_epilogue_kernel");
     return 0;
 }

@@ -29,6 +29,7 @@ struct RegProblem {
     float *loss_f32_out;   // [1] or null
     float *grad_cols_out;  // [n_rows, R] or null
     double *row_loss_out;  // [n_rows, R] or null
+    int *row_sign_out = nullptr;  // [n_rows, R] or null: sum_j sign(a_i - a_j) as the pair kernels classified it
     bool use_triangle = false;  // sorted path, all rows: evaluate constant-sign tiles once for both sides
 };
 
@@ -40,7 +41,7 @@ struct DenseLayout {
     int64_t chunk_cols;    // columns per work unit
     int n_chunks;
     int64_t n_units;
-    size_t off_U, off_A, off_pgrad, off_prow, off_lossp, bytes;
+    size_t off_U, off_A, off_pgrad, off_prow, off_lossp, off_psign, bytes;
 };
 
 DenseLayout dense_layout(int64_t B_total, int64_t n_rows, int R, int sm_count);
@@ -52,23 +53,91 @@ int run_pack_slice(const float *z, int64_t zrs, int64_t zcs, const float *lab, i
 int run_extract_perm(const unsigned long long *keys, int64_t B, int32_t *perm, cudaStream_t st);
 int run_sign_matrix(const float *a, int64_t stride, int64_t B, int8_t *out, cudaStream_t st);
 
+// How sort.cu builds its 64-bit keys (see make_sort_key).
+struct KeySpec {
+    const float *lab;
+    int64_t lrs, lcs;
+    const float *z;      // non-null: segmented keys [outlier:1][sortable attribute:32][index:31] of the reg path
+    int64_t zrs, zcs;
+    float fsign, cabs;   // u = cabs * sgn(f) z decides "outlier" (|u| > kMufu1MaxAbsU)
+    int segment;         // 0: never set the outlier bit (one attribute order per dim)
+    int64_t idx_offset;  // added to the local sample index (row-block shards carry GLOBAL indices)
+    RegDims dims;
+};
+constexpr float kMufu1MaxAbsU = 62.0f;
+constexpr unsigned long long kKeyIdxMask = 0x7FFFFFFFull;  // segmented keys: low 31 bits = sample index
+__host__ __device__ static inline bool key_is_outlier(unsigned long long k) { return (k >> 63) != 0; }
+__host__ __device__ static inline unsigned int key_sortable_attr(unsigned long long k) { return (unsigned int)(k >> 31); }
+
+// ---- row-block sharding over NVLink peer memory (reg_shard.cuh) -------------------------------------------
+constexpr int kMaxShardRanks = 16;
+
+// First bytes of every rank's communication buffer.
+struct ShardHeader {
+    unsigned long long epoch;   // completed sharded steps; a step's kernels signal / wait for epoch + 1
+    int status;                 // != 0: a wait timed out (a peer never signalled); the step's loss comes out NaN
+    unsigned int done_pub, done_pair, done_fin;  // "last CTA" tickets of the publish / pair / finalize kernels
+    long long loss_part[2];     // this rank's exact loss partial (hi, lo), pulled by every peer
+};
+
+// What the kernels of a sharded step need to reach their peers: passed by value.  Every rank's communication buffer
+// has the same layout (offsets below); peer[h] is rank h's buffer as mapped into this process (peer[g] = its own).
+struct ShardView {
+    int G, g;                   // ranks, this rank; G == 0: not a sharded step
+    int R_cap, Gc;              // dims the run slots are sized for; pair-kernel CTAs per rank
+    int64_t n_cap;              // rows a run slot holds
+    int64_t row_off[kMaxShardRanks + 1];  // global index of every rank's first row in this step; [G] = B
+    char *peer[kMaxShardRanks];
+    size_t off_flagA, off_flagB, off_keys, off_xs, off_acc;
+};
+
 // attribute-sorted path (sort.cu, reg_sorted.cu)
 struct SortedLayout {
     int64_t N;      // power-of-two size of the key arrays (sort padding)
     int64_t Bpad;   // columns padded to a multiple of kSubCols
     int n_row_tiles, S;
     int64_t n_rr, F;
-    int G_max, max_segs;
-    size_t slot_bytes;
-    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_cls8, off_cost8, off_combo, off_prefix, off_pgrad, off_prow,
-        off_lossp, off_dbg, off_colpart, off_eloss, bytes;
+    int G_max;
+    size_t acc_bytes;
+    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_cls8, off_cost8, off_combo, off_prefix, off_acc_g, off_acc_l,
+        off_acc_s, off_lossp, off_dbg, off_colpart, off_eloss, bytes;
 };
 int64_t sort_padded_size(int64_t B);
 int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, int64_t B,
                   int64_t N, unsigned long long *keys, cudaStream_t st);
+int run_sort_keys_spec(const KeySpec &spec, int R, int64_t B, int64_t N, unsigned long long *keys, cudaStream_t st);
 SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count, bool with_triangle = false);
 int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStream_t st);
 constexpr int64_t kSortedMinBatch = 8192;  // ARVAE_ALGO_AUTO switches to the sorted path from here
+
+// One rank's state of the sharded step: its NVLink-visible communication buffer, the peers' mappings, a private workspace.
+struct ShardCtx {
+    int G = 0, g = 0, R_cap = 0, device = 0;
+    int64_t n_cap = 0;
+    char *comm = nullptr;       // cudaMalloc'ed here (exported through CUDA IPC)
+    size_t comm_bytes = 0;
+    char *peer[kMaxShardRanks] = {};
+    bool opened[kMaxShardRanks] = {};   // mapped with cudaIpcOpenMemHandle (to be closed)
+    size_t off_flagA = 0, off_flagB = 0, off_keys = 0, off_xs = 0, off_acc = 0;
+    char *ws = nullptr;         // private workspace (sorted columns, plan, ...)
+    size_t ws_bytes = 0, off_mypos = 0;
+    float *h_z = nullptr, *h_lab = nullptr, *h_gz = nullptr, *h_gc = nullptr;  // device staging of the host-buffer entry
+    double *h_loss = nullptr;
+    size_t h_z_bytes = 0, h_lab_bytes = 0, h_gc_bytes = 0;
+};
+struct ShardStep {
+    const float *z; int64_t zrs, zcs;       // this rank's latents [n_local, *]
+    const float *lab; int64_t lrs, lcs;     // this rank's attributes
+    RegDims dims; int R;
+    int64_t n_all[kMaxShardRanks];          // rows of every rank
+    float gamma, factor;
+    double *loss_out; float *loss_f32_out;  // [1] global loss (device)
+    float *grad_cols_out;                   // [n_local, R] or null
+    int phases;                             // bit 0: sort + publish, bit 1: merge + plan + pair kernel, bit 2: finalize; 0 = all
+};
+size_t shard_comm_bytes(int64_t n_cap, int R_cap, int G, ShardCtx *fill);
+size_t shard_ws_bytes(int64_t n_cap, int R_cap, int G, size_t *off_mypos);
+int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st);
 
 // pairwise-rank evaluation metrics (eval_metrics.cu)
 constexpr int kEvalMaxCodes = 1024, kEvalMaxAttrs = 64;

@@ -27,6 +27,7 @@
 //    meeting point), so there is no wave tail and no idle half; row partials are fixed-point integers
 //    written to a (segment, half, row tile) slot: the result does not depend on the split.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "reg_internal.cuh"
@@ -40,13 +41,48 @@ constexpr int kTileThreads = ARVAE_TILE_THREADS;
 constexpr int kTileRI = 4;
 constexpr int kTileRows = kTileThreads * kTileRI;  // 1024 rows per row tile (8 warps x 128 rows; 2 CTAs/SM: best measured)
 constexpr int kStageCols = 2048;                   // columns staged per __syncthreads pair
-constexpr float kMufu1MaxAbsU = 62.0f;
 static_assert(kTileRows / (kTileThreads / 32) == kTileRI * 32, "a warp owns kTileRI x 32 consecutive rows");
 static_assert(kTileThreads / 32 <= 16, "class word holds 16 warps");
+
+// Layout of the small int array `flags` of a call: [0, 32) whole-dim two-MUFU flags (unsegmented keys), [32] plan
+// error, [33, 65) per-dim non-finite latent bits (1: +-inf present, 2: NaN present), [65, 97) n_in per dim.
+constexpr int kFlagError = ARVAE_MAX_REG_DIMS;
+constexpr int kFlagNonFinite = ARVAE_MAX_REG_DIMS + 1;
+constexpr int kFlagNIn = 2 * ARVAE_MAX_REG_DIMS + 1;
+constexpr int kFlagInts = 3 * ARVAE_MAX_REG_DIMS + 1;
+constexpr int kFlagClearInts = kFlagNIn;  // n_in is always written, the rest is cleared per call
+
+// The fixed-point row sums cannot carry NaN, so non-finite latents are flagged when the columns are built and
+// the outputs are patched to what the reference's float arithmetic gives: the loss is NaN, a row with a non-finite
+// latent has a NaN gradient (inf - inf on its diagonal), and a NaN latent poisons every row of its dim.
+__device__ __forceinline__ void note_nonfinite(float xs, int *__restrict__ flags, int r) {
+    if (!(fabsf(xs) < __int_as_float(0x7f800000))) atomicOr(flags + kFlagNonFinite + r, xs != xs ? 2 : 1);
+}
+__device__ __forceinline__ bool row_is_poisoned(const int *__restrict__ flags, int r, float xs) {
+    const int nf = flags[kFlagNonFinite + r];
+    return nf != 0 && ((nf & 2) || !(fabsf(xs) < __int_as_float(0x7f800000)));
+}
+__device__ __forceinline__ bool any_nonfinite(const int *__restrict__ flags, int R) {
+    int nf = flags[kFlagError];
+    for (int r = 0; r < R; ++r) nf |= flags[kFlagNonFinite + r];
+    return nf != 0;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // gather the sorted order: Us/As/Es[r][k] for sorted position k, perm[r][k] = original index
 // ------------------------------------------------------------------------------------------------
+// Sorted order of a dim (sort.cu, segmented keys): [inliers by attribute | outliers by attribute | padding].
+// n_in[r] = number of inliers = the first position of the outlier segment.  Exactly one thread per dim sees the
+// segment boundary and writes it (no atomics, no memset).
+__device__ __forceinline__ void note_segment_boundary(const unsigned long long *__restrict__ kr, int64_t k, int64_t B,
+                                                      int *__restrict__ n_in_r) {
+    if (k >= B) return;
+    const bool out_here = key_is_outlier(kr[k]);
+    if (k == 0 && out_here) *n_in_r = 0;
+    if (!out_here && (k + 1 == B || key_is_outlier(kr[k + 1]))) *n_in_r = (int)(k + 1);
+}
+
 __global__ void __launch_bounds__(256)
 sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
                      const float *__restrict__ z, int64_t zrs, int64_t zcs,
@@ -54,25 +90,32 @@ sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
                      int64_t B, int64_t Bpad, float fsign, float cabs, float *__restrict__ Xs,
                      float *__restrict__ As, float *__restrict__ Es, int *__restrict__ perm,
                      int *__restrict__ flags, int64_t row_begin, int64_t row_end,
-                     int *__restrict__ blockcnt) {
+                     int *__restrict__ blockcnt, int unsegmented) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
+    const unsigned long long *kr = keys + (int64_t)r * N;
     int mine = 0;
-    if (k < B) mine = ((int64_t)(unsigned int)(keys[(int64_t)r * N + k] & 0xFFFFFFFFull) >= row_begin &&
-                       (int64_t)(unsigned int)(keys[(int64_t)r * N + k] & 0xFFFFFFFFull) < row_end);
+    if (k < B) {
+        const int64_t idx = (int64_t)(kr[k] & kKeyIdxMask);
+        mine = idx >= row_begin && idx < row_end;
+    }
     const int cnt = __syncthreads_count(mine);  // rows of this call among this CTA's 256 sorted positions
     if (blockcnt && threadIdx.x == 0) blockcnt[(int64_t)r * gridDim.x + blockIdx.x] = cnt;
     if (k >= Bpad) return;
     const int64_t o = (int64_t)r * Bpad + k;
     if (k < B) {
-        const int64_t idx = (int64_t)(unsigned int)(keys[(int64_t)r * N + k] & 0xFFFFFFFFull);
+        const unsigned long long key = kr[k];
+        const int64_t idx = (int64_t)(key & kKeyIdxMask);
         const float xs = signed_latent(__ldg(z + idx * zrs + (int64_t)dims.zcol[r] * zcs), fsign);
-        const float u = cabs * xs;
         Xs[o] = xs;
         As[o] = __ldg(lab + idx * lrs + (int64_t)dims.lcol[r] * lcs);
-        Es[o] = exp2f(u);
+        const float u = cabs * xs;
+        Es[o] = key_is_outlier(key) ? 1.0f : exp2f(u);  // outliers never take the factorised form
         perm[o] = (int)idx;
-        if (!(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + r, 1);  // also catches NaN / inf
+        // unsegmented keys (triangle mode): one out-of-range element sends the whole dim to the two-MUFU form
+        if (unsegmented && !(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + r, 1);
+        note_nonfinite(xs, flags, r);
+        note_segment_boundary(kr, k, B, flags + kFlagNIn + r);
     } else {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
         Xs[o] = ARVAE_PAD_U;
         As[o] = ARVAE_PAD_A;
@@ -128,9 +171,11 @@ row_select_kernel(const int *__restrict__ perm, const int *__restrict__ blockcnt
 typedef long long acc_t;
 constexpr double kFixMagic = 6291456.0;              // 1.5 * 2^22: (v + magic) keeps round(v 2^30) in the mantissa
 constexpr double kFixScale = 1.0 / 1073741824.0;     // 2^-30
-// per-CTA loss partials drop 6 bits (2^-24): 6 B^2 R / #CTAs stays far below 2^63 up to B ~ 10^6
-constexpr int kLossShift = 6;
-constexpr double kLossScale = 1.0 / 16777216.0;      // 2^-24
+// Loss partials are carried as two exact integers (v >> 20 and v & (2^20 - 1)) so that neither can overflow and their
+// totals -- hence the loss -- do not depend on how the pair work was split over CTAs, halves or GPUs.
+constexpr int kLossSplitBits = 20;
+constexpr long long kLossLoMask = (1LL << kLossSplitBits) - 1;
+constexpr double kLossHiScale = 1.0 / 1024.0;        // 2^20 * 2^-30
 __device__ __forceinline__ void acc_add(acc_t &acc, float v) {
     acc += __double_as_longlong((double)v + kFixMagic) - __double_as_longlong(kFixMagic);
 }
@@ -246,14 +291,14 @@ __device__ __forceinline__ void loop_tie(const RowRegs &R, const float *__restri
     }
 }
 
-template <bool MUFU1, bool GRAD, int ncols = kSubCols>
+template <bool MUFU1, bool GRAD, int ncols = kSubCols, bool SIGNS = false>
 __device__ __forceinline__ void loop_general(const RowRegs &R, const float *__restrict__ se,
                                              const float *__restrict__ sx,
                                              const float *__restrict__ sa, float cabs,
-                                             acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
-    float lacc[kTileRI], gacc[kTileRI];
+                                             acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], int *ds = nullptr) {
+    float lacc[kTileRI], gacc[kTileRI], kacc[kTileRI];
 #pragma unroll
-    for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = 0.0f;
+    for (int k = 0; k < kTileRI; ++k) lacc[k] = gacc[k] = kacc[k] = 0.0f;
 #pragma unroll 2
     for (int q = 0; q < ncols; q += 4) {
         const float4 xj = *reinterpret_cast<const float4 *>(sx + q);
@@ -276,6 +321,7 @@ __device__ __forceinline__ void loop_general(const RowRegs &R, const float *__re
                 const float kk = (1.0f - gt) + lt;  // 1 - s
                 const float v = fmaf(-2.0f, r, kk);
                 lacc[k] += fabsf(v);
+                if (SIGNS) kacc[k] += kk;  // small integers: exact
                 if (GRAD) {
                     const float w4 = fmaf(-r, r, r);
                     // sgn(v): -s when s != 0, else sgn(d) (see reg_dense.cu: pair_general)
@@ -290,6 +336,7 @@ __device__ __forceinline__ void loop_general(const RowRegs &R, const float *__re
     for (int k = 0; k < kTileRI; ++k) {
         acc_add(dl[k], lacc[k]);
         if (GRAD) acc_add(dg[k], gacc[k]);
+        if (SIGNS) ds[k] += ncols - (int)kacc[k];  // sum_j s_ij = n - sum_j (1 - s_ij), from the very compares the loss used
     }
 }
 
@@ -312,25 +359,31 @@ struct TilesArgs {
     const float *Xs, *Es, *As;  // [R][Bpad] in sorted order: sgn(f) x, 2^u, attribute
     float cabs;                 // |2 f log2(e)|
     const int *rowpos;          // [R][n_rows] sorted positions of this call's rows, or null = identity
-    const int *flags;           // [R] non-zero: some |u| > 62, use the 2-MUFU form for this dim
+    const int *flags;           // small per-call flags (layout above): [r] non-zero = the WHOLE dim uses the 2-MUFU form
+    const int *n_in;            // [R] number of inliers = first sorted position of the outlier segment
     int64_t Bpad, n_rows;
     int n_row_tiles, S;         // S = Bpad / kSubCols sub-chunks per row tile
     int P;                      // sub-chunk visiting stride (coprime to S)
     int64_t F;                  // fine units = R * n_row_tiles * S
-    int G;                      // persistent CTAs
+    int G;                      // persistent CTAs the plan is cut into (all GPUs of a sharded step together)
+    int c_first;                // first of those CTAs this launch runs (0 on a single GPU)
     int64_t n_rr;               // R * n_row_tiles
     int force_general;          // treat every tile as general (unsorted input / debugging)
     // plan (plan_classes_kernel / plan_scan_kernel): per fine unit in VISITING order u = rr * S + s'
-    unsigned int *cls8;         // [F] 2-bit tile class per warp (bits 2w..2w+1, up to 16 warps)
+    unsigned int *cls8;         // [F] per warp w: 2-bit tile class (bits 2w..2w+1) and tanh form (bit 16+w: 1 = two MUFU)
     unsigned short *cost8;      // [F] modelled cost of the unit (sum over the tile's warps)
     long long *prefix;          // [n_rr + 1] exclusive prefix of the per-row-tile cost totals; [n_rr] = T
-    acc_t *pgrad, *prow, *lossp;  // fixed-point row partials per slot; per-CTA loss partials
+    // fixed-point row accumulators, indexed [rr * kTileRows + row within tile]; integer atomics: order-free
+    acc_t *acc_g, *acc_l;       // gradient / loss row sums (acc_l only when per-row losses are wanted)
+    int *acc_s;                 // sum_j sign(a_i - a_j) per row (parity instrumentation), or null
+    acc_t *lossp;               // [launch CTAs][2] per-CTA loss partials (hi, lo)
     unsigned long long *dbg_times;  // [G][2] globaltimer at CTA start / end (experiments), or null
     // triangle mode (reg_tri.cuh)
     float2 *colpart;            // per (row tile, column at or above it): column sums (sum r, sum r^2) of double-duty tiles
     int Pinv;                   // inverse of P modulo S
     int64_t B;                  // number of real columns (= rows in triangle mode)
-    int max_segs;               // segment slots per row tile
+    ShardView shard;            // sharded step (shard.G > 0): the last CTA publishes this GPU's loss partial and signals
+                                // its peers (reg_shard.cuh)
 };
 
 // Work split: unit u starts at cost position p(u) (exclusive prefix of the modelled costs in visiting
@@ -351,39 +404,54 @@ __device__ __forceinline__ int class_cost(int cls, bool mufu1) {
 
 // One CTA per row tile rr: class byte and cost of each of its S units (in visiting order), and the
 // row tile's total cost.
+//
+// Tanh form per (warp, unit): the factorised one-MUFU form needs every element of the tile to be an inlier
+// (|u| <= 62): the warp's rows must all lie before n_in[r] and so must the sub-chunk's real columns.  A warp's row
+// group or a sub-chunk that straddles the inlier / outlier boundary is not attribute-sorted across it, so its end
+// points say nothing about its range: such tiles run the general loop.
 __global__ void __launch_bounds__(256)
 plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost) {
     __shared__ float wmin[kTileThreads / 32], wmax[kTileThreads / 32];
-    __shared__ int whas[kTileThreads / 32];
+    __shared__ int whas[kTileThreads / 32], win[kTileThreads / 32], wmixed[kTileThreads / 32];
     __shared__ int sred[8];
     const int64_t rr = blockIdx.x;
     const int r = (int)(rr / a.n_row_tiles), I = (int)(rr % a.n_row_tiles);
     const float *Ar = a.As + (int64_t)r * a.Bpad;
     const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
-    const bool mufu1 = a.flags[r] == 0;
+    const bool dim_mufu1 = a.flags[r] == 0;
+    const int64_t nin = a.n_in[r];
     constexpr int kWarpRows = kTileRows / (kTileThreads / 32);
     if (threadIdx.x < kTileThreads / 32) {
         const int64_t m0 = (int64_t)I * kTileRows + (int64_t)threadIdx.x * kWarpRows;
         const int64_t ml = min(m0 + kWarpRows, a.n_rows) - 1;
         const bool has = m0 < a.n_rows;
+        const int64_t p0 = has ? (rp ? (int64_t)rp[m0] : m0) : 0, pl = has ? (rp ? (int64_t)rp[ml] : ml) : 0;
         whas[threadIdx.x] = has;
-        wmin[threadIdx.x] = has ? Ar[rp ? rp[m0] : m0] : 0.0f;
-        wmax[threadIdx.x] = has ? Ar[rp ? rp[ml] : ml] : 0.0f;
+        wmin[threadIdx.x] = has ? Ar[p0] : 0.0f;
+        wmax[threadIdx.x] = has ? Ar[pl] : 0.0f;
+        win[threadIdx.x] = pl < nin;                 // every row of the warp is an inlier
+        wmixed[threadIdx.x] = p0 < nin && pl >= nin;  // rows from both segments
     }
     __syncthreads();
     int total = 0;
     for (int sp = threadIdx.x; sp < a.S; sp += 256) {
         const int64_t col = (((int64_t)sp * a.P) % a.S) * kSubCols;
         const float cmin = Ar[col], cmax = Ar[col + kSubCols - 1];
-        unsigned int cls8 = 0;
+        const int64_t col_last_real = min(col + kSubCols, a.B) - 1;  // < col: pure padding (works in either form)
+        const bool col_in = col_last_real < nin || col_last_real < col;
+        const bool col_mixed = col < nin && col_last_real >= nin;
+        unsigned int word = 0;
         int cost = 0;
 #pragma unroll
         for (int w = 0; w < kTileThreads / 32; ++w) {
-            const int cls = a.force_general ? (int)kClassGeneral : classify(wmin[w], wmax[w], cmin, cmax);
-            cls8 |= (unsigned int)cls << (2 * w);
+            const bool general = a.force_general || wmixed[w] || col_mixed;
+            const int cls = general ? (int)kClassGeneral : classify(wmin[w], wmax[w], cmin, cmax);
+            const bool mufu1 = dim_mufu1 && win[w] && col_in;
+            word |= (unsigned int)cls << (2 * w);
+            word |= (mufu1 ? 0u : 1u) << (16 + w);
             if (whas[w]) cost += class_cost(cls, mufu1);
         }
-        a.cls8[rr * a.S + sp] = cls8;
+        a.cls8[rr * a.S + sp] = word;
         a.cost8[rr * a.S + sp] = (unsigned short)cost;
         total += cost;
     }
@@ -490,14 +558,27 @@ __device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, 
     __syncthreads();
 }
 
-template <bool MUFU1, bool GRAD>
+template <bool MUFU1, bool GRAD, bool SIGNS>
 __device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const float *se,
                                                const float *sx, const float *sa, float cabs,
-                                               acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
-    if (cls == kClassPos) loop_const<MUFU1, GRAD>(R, se, sx, cabs, true, dl, dg);
-    else if (cls == kClassNeg) loop_const<MUFU1, GRAD>(R, se, sx, cabs, false, dl, dg);
-    else if (cls == kClassTie) loop_tie<MUFU1, GRAD>(R, se, sx, cabs, dl, dg);
-    else loop_general<MUFU1, GRAD>(R, se, sx, sa, cabs, dl, dg);
+                                               acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], int (&ds)[kTileRI]) {
+    if (cls == kClassPos) {
+        loop_const<MUFU1, GRAD>(R, se, sx, cabs, true, dl, dg);
+        if (SIGNS) {
+#pragma unroll
+            for (int k = 0; k < kTileRI; ++k) ds[k] += kSubCols;
+        }
+    } else if (cls == kClassNeg) {
+        loop_const<MUFU1, GRAD>(R, se, sx, cabs, false, dl, dg);
+        if (SIGNS) {
+#pragma unroll
+            for (int k = 0; k < kTileRI; ++k) ds[k] -= kSubCols;
+        }
+    } else if (cls == kClassTie) {
+        loop_tie<MUFU1, GRAD>(R, se, sx, cabs, dl, dg);
+    } else {
+        loop_general<MUFU1, GRAD, kSubCols, SIGNS>(R, se, sx, sa, cabs, dl, dg, ds);
+    }
 }
 
 // The pair kernel.  One CTA of 512 threads per SM, split into two independent halves of 8 warps (256 threads,
@@ -506,8 +587,10 @@ __device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const 
 // claiming a few units at a time from a shared counter until they meet.  Whichever half the SM's warp
 // arbitration favours simply takes more units, so both stay busy to the end (with two independent CTAs per
 // SM and a static split the favoured CTA finished at ~55 % of the kernel and the other ran alone, at lower
-// MUFU utilisation, for the rest).  Row partials are fixed-point integers, so the result does not depend on
-// where the halves meet.
+// MUFU utilisation, for the rest).  Row partials are fixed-point integers added to per-row accumulators with
+// integer atomics, so the result does not depend on where the halves meet, on the number of CTAs, or -- in a
+// sharded step, where this launch runs CTAs [c_first, c_first + gridDim.x) of a plan cut into G -- on the number
+// of GPUs.
 constexpr int kDuoThreads = 2 * kTileThreads;
 constexpr int kStageSubs = kStageCols / kSubCols;
 constexpr int kDuoStageBytes = 2 * 3 * kStageCols * (int)sizeof(float);  // 48 KiB
@@ -516,21 +599,23 @@ __device__ __forceinline__ void half_barrier(int half) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(kTileThreads) : "memory");
 }
 
-template <bool GRAD>
+__device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh);  // reg_shard.cuh
+
+template <bool GRAD, bool SIGNS>
 __global__ void __launch_bounds__(kDuoThreads, 1)
 reg_tiles_kernel(TilesArgs a) {
     extern __shared__ __align__(16) float stage[];  // [2 halves][3 arrays][kStageCols] = kDuoStageBytes (dynamic)
-    __shared__ acc_t sred[kDuoThreads / 32];
+    __shared__ acc_t sred[2][kDuoThreads / 32];
     __shared__ int s_rng[4];
     __shared__ int s_scan[kDuoThreads];
     __shared__ unsigned int s_claimed;   // units granted so far (may overshoot N)
     __shared__ int s_grant[2][2];        // per half: first unit (linear) and count of the current grant
 
-    const long long c = blockIdx.x;
+    const long long c = (long long)a.c_first + blockIdx.x;
     if (a.dbg_times && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        a.dbg_times[2 * c] = t;
+        a.dbg_times[2 * blockIdx.x] = t;
     }
     if (threadIdx.x == 0) s_claimed = 0u;
     const long long T = a.prefix[a.n_rr];
@@ -549,34 +634,33 @@ reg_tiles_kernel(TilesArgs a) {
 
     int64_t cursor = half == 0 ? 0 : N;  // next unit from the front / one past the next unit from the back
     int64_t cur_rr = -1;
-    acc_t lthread = 0;
+    acc_t lhi = 0, llo = 0;
     RowRegs R;
     bool valid[kTileRI];
     acc_t dl[kTileRI], dg[kTileRI];
-    bool warp_has_rows = false, mufu1 = true;
+    int ds[kTileRI];
+    bool warp_has_rows = false;
     const float *Er = nullptr, *Xr = nullptr, *Ar = nullptr;
 #pragma unroll
-    for (int k = 0; k < kTileRI; ++k) { valid[k] = false; dl[k] = 0; dg[k] = 0; R.e[k] = 1.0f; R.x[k] = 0.0f; R.a[k] = 0.0f; }
+    for (int k = 0; k < kTileRI; ++k) { valid[k] = false; dl[k] = 0; dg[k] = 0; ds[k] = 0; R.e[k] = 1.0f; R.x[k] = 0.0f; R.a[k] = 0.0f; }
 
-    // flush this half's partial sums of row tile cur_rr into its slot (segment of this CTA, half)
+    // add this half's partial sums of row tile cur_rr to the row accumulators
     auto flush = [&]() {
         if (cur_rr < 0) return;
-        int64_t seg = c - owner_of_pos(a.prefix[cur_rr], T, a.G);
-        if (seg >= a.max_segs) {  // cannot happen within the modelled cost ratios; never write out of bounds
-            if (tid == 0) atomicExch(const_cast<int *>(a.flags) + ARVAE_MAX_REG_DIMS, 1);  // epilogue reports NaN
-            seg = a.max_segs - 1;
-        }
-        const int64_t slot = (((seg * 2 + half) * a.n_rr) + cur_rr) * kTileRows;
+        const int64_t base = cur_rr * kTileRows + warp * kWarpRows + lane;
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
-            const int64_t o = slot + warp * kWarpRows + k * 32 + lane;  // = row - tile start
+            const int64_t o = base + k * 32;  // rr * kTileRows + (row - tile start)
             if (valid[k]) {
-                lthread += dl[k] >> kLossShift;
-                if (GRAD) a.pgrad[o] = dg[k];
-                if (a.prow) a.prow[o] = dl[k];
+                lhi += dl[k] >> kLossSplitBits;
+                llo += dl[k] & kLossLoMask;
+                if (GRAD && dg[k] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.acc_g + o), (unsigned long long)dg[k]);
+                if (a.acc_l && dl[k] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.acc_l + o), (unsigned long long)dl[k]);
+                if (SIGNS && ds[k] != 0) atomicAdd(a.acc_s + o, ds[k]);
             }
             dl[k] = 0;
             dg[k] = 0;
+            ds[k] = 0;
         }
     };
 
@@ -614,7 +698,6 @@ reg_tiles_kernel(TilesArgs a) {
             cur_rr = rr;
             const int r = (int)(rr / a.n_row_tiles);
             const int I = (int)(rr % a.n_row_tiles);
-            mufu1 = a.flags[r] == 0;
             Er = a.Es + (int64_t)r * a.Bpad;
             Xr = a.Xs + (int64_t)r * a.Bpad;
             Ar = a.As + (int64_t)r * a.Bpad;
@@ -646,34 +729,59 @@ reg_tiles_kernel(TilesArgs a) {
         if (warp_has_rows) {
             for (int w = 0; w < nsub; ++w) {
                 const int sub = w * kSubCols;
-                const int cls = (a.cls8[rr * a.S + sp + w] >> (2 * warp)) & 3;  // planned class of this warp's tile
-                if (mufu1) sweep_subchunk<true, GRAD>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg);
-                else sweep_subchunk<false, GRAD>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg);
+                const unsigned int word = a.cls8[rr * a.S + sp + w];
+                const int cls = (word >> (2 * warp)) & 3;        // planned class of this warp's tile
+                const bool mufu1 = ((word >> (16 + warp)) & 1u) == 0u;  // planned tanh form
+                if (mufu1) sweep_subchunk<true, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
+                else sweep_subchunk<false, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
             }
         }
     }
     flush();
 
-    lthread = warp_sum(lthread);
-    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = lthread;
+    lhi = warp_sum(lhi);
+    llo = warp_sum(llo);
+    if ((threadIdx.x & 31) == 0) { sred[0][threadIdx.x >> 5] = lhi; sred[1][threadIdx.x >> 5] = llo; }
+    if (a.shard.G > 0) __threadfence_system();  // this thread's row-accumulator atomics are visible to the peers before the signal
     __syncthreads();
     if (threadIdx.x == 0) {
-        acc_t t = 0;
+        acc_t th = 0, tl = 0;
 #pragma unroll
-        for (int w = 0; w < kDuoThreads / 32; ++w) t += sred[w];
-        a.lossp[c] = t;
+        for (int w = 0; w < kDuoThreads / 32; ++w) { th += sred[0][w]; tl += sred[1][w]; }
+        a.lossp[2 * blockIdx.x] = th;
+        a.lossp[2 * blockIdx.x + 1] = tl;
         if (a.dbg_times) {
             unsigned long long tt;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
-            a.dbg_times[2 * c + 1] = tt;
+            a.dbg_times[2 * blockIdx.x + 1] = tt;
         }
     }
+    if (a.shard.G > 0) shard_pair_kernel_tail(a, reinterpret_cast<acc_t *>(stage));
+}
+
+// Loss of a launch from its per-CTA (hi, lo) partials: exact integer totals, one rounding at the end.
+__device__ __forceinline__ void sum_loss_partials(const acc_t *__restrict__ lossp, int64_t n_cta, acc_t *sh /*smem [2][256]*/,
+                                                  acc_t &hi, acc_t &lo) {
+    acc_t th = 0, tl = 0;
+    for (int64_t u = threadIdx.x; u < n_cta; u += blockDim.x) { th += lossp[2 * u]; tl += lossp[2 * u + 1]; }
+    sh[threadIdx.x] = th;
+    sh[256 + threadIdx.x] = tl;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh[threadIdx.x] += sh[threadIdx.x + o]; sh[256 + threadIdx.x] += sh[256 + threadIdx.x + o]; }
+        __syncthreads();
+    }
+    hi = sh[0];
+    lo = sh[256];
+}
+__device__ __forceinline__ double loss_from_hilo(acc_t hi, acc_t lo) {
+    return (double)hi * kLossHiScale + (double)lo * kFixScale;
 }
 
 __global__ void __launch_bounds__(256)
-reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int64_t row_begin,
+reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int64_t row_begin, int n_cta,
                           double gscale, double lscale, double pad_per_row,
-                          float *__restrict__ grad_cols, double *__restrict__ row_loss,
+                          float *__restrict__ grad_cols, double *__restrict__ row_loss, int *__restrict__ row_sign,
                           double *__restrict__ loss_out, float *__restrict__ loss_f32_out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over R * n_rows, m fastest
     if (idx < (int64_t)R * a.n_rows) {
@@ -681,36 +789,21 @@ reg_tiles_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, int6
         const int64_t m = idx % a.n_rows;
         const int64_t I = m / kTileRows, lr = m % kTileRows;
         const int64_t rr = (int64_t)r * a.n_row_tiles + I;
-        const long long T = a.prefix[a.n_rr];
-        const int64_t c0 = owner_of_pos(a.prefix[rr], T, a.G);
-        const int64_t c1 = owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G);
-        const int64_t nslot = 2 * min(c1 - c0 + 1, (int64_t)a.max_segs);  // (segment, half) slots; unused ones are zero
         const int64_t pos = a.rowpos ? (int64_t)a.rowpos[(int64_t)r * a.n_rows + m] : m;
         const int64_t out = ((int64_t)perm[(int64_t)r * a.Bpad + pos] - row_begin) * R + r;
-        if (grad_cols) {
-            acc_t g = 0;
-            for (int64_t sl = 0; sl < nslot; ++sl) g += a.pgrad[(sl * a.n_rr + rr) * kTileRows + lr];
-            grad_cols[out] = (float)((double)g * kFixScale * gscale);
-        }
-        if (row_loss) {
-            acc_t l = 0;
-            for (int64_t sl = 0; sl < nslot; ++sl) l += a.prow[(sl * a.n_rr + rr) * kTileRows + lr];
-            row_loss[out] = (double)l * kFixScale - pad_per_row;
-        }
+        const bool poisoned = row_is_poisoned(a.flags, r, a.Xs[(int64_t)r * a.Bpad + pos]);
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        if (grad_cols) grad_cols[out] = poisoned ? (float)nan : (float)((double)a.acc_g[rr * kTileRows + lr] * kFixScale * gscale);
+        if (row_loss) row_loss[out] = poisoned ? nan : (double)a.acc_l[rr * kTileRows + lr] * kFixScale - pad_per_row;
+        if (row_sign) row_sign[out] = a.acc_s[rr * kTileRows + lr];
     }
     if (blockIdx.x == 0) {
-        __shared__ double sh[256];
-        double t = 0.0;
-        for (int64_t u = threadIdx.x; u < a.G; u += 256) t += (double)a.lossp[u] * kLossScale;  // fixed order
-        sh[threadIdx.x] = t;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-            __syncthreads();
-        }
+        __shared__ acc_t sh[512];
+        acc_t hi, lo;
+        sum_loss_partials(a.lossp, n_cta, sh, hi, lo);
         if (threadIdx.x == 0) {
-            double total = sh[0] - pad_per_row * (double)a.n_rows * (double)R;
-            if (a.flags[ARVAE_MAX_REG_DIMS]) total = __longlong_as_double(0x7ff8000000000000LL);  // slot overflow: NaN, not a wrong number
+            double total = loss_from_hilo(hi, lo) - pad_per_row * (double)a.n_rows * (double)R;
+            if (any_nonfinite(a.flags, R)) total = __longlong_as_double(0x7ff8000000000000LL);  // as the reference's float sum
             *loss_out = total * lscale;
             if (loss_f32_out) *loss_f32_out = (float)(total * lscale);
         }
@@ -739,16 +832,16 @@ static int current_device_slot() {
 }
 
 // CTAs of the pair kernel that fit one SM (1 with its 512 threads x 128 registers); also opts the kernel into
-// 48 KiB of dynamic shared memory.  Function attributes are per device: cached per (device, variant).
-static int tiles_ctas_per_sm(bool grad) {
-    static int cache[64][2] = {};
-    int &v = cache[current_device_slot()][grad ? 1 : 0];
+// 48 KiB of dynamic shared memory.  Function attributes are per device: cached per device.
+static int tiles_ctas_per_sm() {
+    static int cache[64] = {};
+    int &v = cache[current_device_slot()];
     if (v == 0) {
         int n = 0;
-        cudaFuncSetAttribute(reg_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
-        cudaFuncSetAttribute(reg_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
-        cudaError_t e = grad ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<true>, kDuoThreads, kDuoStageBytes)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<false>, kDuoThreads, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<true, false>, kDuoThreads, kDuoStageBytes);
         if (e != cudaSuccess || n <= 0) {
             (void)cudaGetLastError();
             n = 1;
@@ -756,6 +849,19 @@ static int tiles_ctas_per_sm(bool grad) {
         v = n;
     }
     return v;
+}
+
+static void launch_tiles(const TilesArgs &a, int n_cta, bool want_grad, bool want_signs, cudaStream_t st) {
+    if (want_signs) reg_tiles_kernel<true, true><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+    else if (want_grad) reg_tiles_kernel<true, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+    else reg_tiles_kernel<false, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+}
+
+void reg_scales(const RegProblem &P, int64_t Bpad, double &lscale, double &gscale, double &pad_per_row) {
+    const double BB = (double)P.B * (double)P.B;
+    lscale = (double)P.gamma / BB;
+    gscale = 8.0 * (double)P.gamma * (double)P.factor / BB;
+    pad_per_row = (double)(Bpad - P.B);
 }
 
 #include "reg_tri.cuh"
@@ -768,18 +874,11 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
     L.S = (int)(L.Bpad / kSubCols);
     L.n_rr = (int64_t)R * L.n_row_tiles;
     L.F = L.n_rr * L.S;
-    // the larger occupancy of the two kernel variants bounds the slot count for both
     const int per_sm = 2;  // the pair kernel runs 1 CTA (two halves) per SM, the triangle variant 2 CTAs per SM
     int64_t G = (int64_t)sm_count * per_sm;
     if (G > L.F / 4) G = L.F / 4;  // >= 4 units per CTA on average: every CTA owns at least one unit
     L.G_max = (int)(G > 0 ? G : 1);
-    // a row tile's share of the CTAs is at most (max unit cost / min unit cost) = 2.5 x the average
-    L.max_segs = (int)((5 * (int64_t)L.G_max + 2 * L.n_rr - 1) / (2 * L.n_rr) + 2);
     const bool tri_capable = with_triangle && (n_rows == B_total && B_total > 0);
-    if (tri_capable) {  // triangle mode: per-row-tile costs vary more (the first row tile has ~2x the average)
-        const int tri_segs = (int)((4 * (int64_t)L.G_max + L.n_rr - 1) / L.n_rr + 3);
-        if (tri_segs > L.max_segs) L.max_segs = tri_segs;
-    }
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -792,16 +891,18 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
     L.off_Es = take(sizeof(float) * (size_t)R * L.Bpad);
     L.off_perm = take(sizeof(int) * (size_t)R * L.Bpad);
     L.off_rowpos = take(sizeof(int) * (size_t)R * (n_rows > 0 ? n_rows : 1));
-    L.off_flags = take(sizeof(int) * (ARVAE_MAX_REG_DIMS + 1));  // [R] range-guard flags + one overflow flag
+    L.off_flags = take(sizeof(int) * kFlagInts);
     L.off_blockcnt = take(sizeof(int) * (size_t)R * (size_t)ceil_div(L.Bpad, 256));
     L.off_cls8 = take(sizeof(unsigned int) * (size_t)L.F);
     L.off_cost8 = take(sizeof(unsigned short) * (size_t)L.F);
     L.off_combo = take(sizeof(int) * (size_t)L.n_rr);
     L.off_prefix = take(sizeof(long long) * (size_t)(L.n_rr + 1));
-    L.slot_bytes = sizeof(acc_t) * 2 * (size_t)L.max_segs * L.n_rr * kTileRows;  // (segment, half) slots per row tile
-    L.off_pgrad = take(L.slot_bytes);
-    L.off_prow = take(L.slot_bytes);
-    L.off_lossp = take(sizeof(acc_t) * (size_t)L.G_max);
+    // row accumulators: gradient, loss, sign sums -- contiguous so that one memset clears the ones in use
+    L.acc_bytes = sizeof(acc_t) * (size_t)L.n_rr * kTileRows;
+    L.off_acc_g = take(L.acc_bytes);
+    L.off_acc_l = take(L.acc_bytes);
+    L.off_acc_s = take(sizeof(int) * (size_t)L.n_rr * kTileRows);
+    L.off_lossp = take(sizeof(acc_t) * 2 * (size_t)L.G_max);
     L.off_colpart = take(tri_capable ? sizeof(float2) * (size_t)R * (size_t)colpart_size(L.n_row_tiles, L.Bpad) : 0);
     L.off_eloss = take(sizeof(double) * (size_t)(ceil_div((n_rows > 0 ? n_rows : 1) * (int64_t)R, 256)));
     L.off_dbg = take(sizeof(unsigned long long) * 2 * (size_t)L.G_max);
@@ -817,21 +918,38 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     int *perm = reinterpret_cast<int *>(ws + L.off_perm);
     int *rowpos = reinterpret_cast<int *>(ws + L.off_rowpos);
     int *flags = reinterpret_cast<int *>(ws + L.off_flags);
+    int *n_in = flags + kFlagNIn;
     int *blockcnt = reinterpret_cast<int *>(ws + L.off_blockcnt);
     const int64_t n_rows = P.row_end - P.row_begin;
     const bool want_grad = P.grad_cols_out != nullptr;
+    const bool want_signs = P.row_sign_out != nullptr;
     const bool all_rows = (P.row_begin == 0 && P.row_end == P.B);
+    const bool triangle = P.use_triangle && all_rows && n_rows > 0;
+    if (want_signs && (triangle || !want_grad)) {
+        set_error("row sign sums need the gradient pass of the dense or sorted algorithm");
+        return ARVAE_E_BADARG;
+    }
 
-    int rc = run_sort_keys(P.lab, P.lrs, P.lcs, P.dims, P.R, P.B, L.N, keys, st);
-    if (rc) return rc;
-    ARVAE_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * (ARVAE_MAX_REG_DIMS + 1), st));
     const double c = 2.0 * (double)P.factor * 1.4426950408889634074;  // 2 f log2(e)
     const float fsign = P.factor > 0.f ? 1.0f : (P.factor < 0.f ? -1.0f : 0.0f);
     const float cabs = P.factor != 0.f ? (float)fabs(c) : 1.0f;  // f == 0: xs == 0, any scale works
+    KeySpec spec;
+    spec.lab = P.lab; spec.lrs = P.lrs; spec.lcs = P.lcs;
+    spec.z = P.z; spec.zrs = P.zrs; spec.zcs = P.zcs;
+    spec.fsign = fsign;
+    spec.cabs = cabs;
+    // triangle mode needs ONE attribute order per dim: no outlier segment there, the whole dim falls back to the
+    // two-MUFU form instead (sorted_gather_kernel's dimflags)
+    spec.segment = triangle ? 0 : 1;
+    spec.idx_offset = 0;
+    spec.dims = P.dims;
+    int rc = run_sort_keys_spec(spec, P.R, P.B, L.N, keys, st);
+    if (rc) return rc;
+    ARVAE_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * kFlagClearInts, st));
     dim3 gg((unsigned)ceil_div(L.Bpad, 256), (unsigned)P.R);
     sorted_gather_kernel<<<gg, 256, 0, st>>>(keys, L.N, P.z, P.zrs, P.zcs, P.lab, P.lrs, P.lcs, P.dims,
                                              P.B, L.Bpad, fsign, cabs, Xs, As, Es, perm, flags,
-                                             P.row_begin, P.row_end, all_rows ? nullptr : blockcnt);
+                                             P.row_begin, P.row_end, all_rows ? nullptr : blockcnt, triangle ? 1 : 0);
     ARVAE_LAUNCH_CHECK("sorted_gather_kernel");
     if (!all_rows && n_rows > 0) {
         dim3 gs((unsigned)ceil_div(L.Bpad, 1024), (unsigned)P.R);
@@ -841,57 +959,61 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     }
 
     TilesArgs a;
+    memset(&a, 0, sizeof(a));
     a.Xs = Xs; a.Es = Es; a.As = As;
     a.cabs = cabs;
     a.rowpos = all_rows ? nullptr : rowpos;
     a.flags = flags;
+    a.n_in = n_in;
     a.Bpad = L.Bpad; a.n_rows = n_rows;
     a.n_row_tiles = L.n_row_tiles; a.S = L.S; a.F = L.F; a.n_rr = L.n_rr;
     a.P = golden_stride(L.S);
-    int64_t G = (int64_t)sm_count() * tiles_ctas_per_sm(want_grad);
+    int64_t G = (int64_t)sm_count() * tiles_ctas_per_sm();
     if (G > L.G_max) G = L.G_max;
     if (G < 1) G = 1;
     a.G = (int)G;
+    a.c_first = 0;
     a.force_general = 0;
     a.cls8 = reinterpret_cast<unsigned int *>(ws + L.off_cls8);
     a.cost8 = reinterpret_cast<unsigned short *>(ws + L.off_cost8);
     a.prefix = reinterpret_cast<long long *>(ws + L.off_prefix);
     int *combo_cost = reinterpret_cast<int *>(ws + L.off_combo);
-    a.pgrad = reinterpret_cast<acc_t *>(ws + L.off_pgrad);
-    a.prow = P.row_loss_out ? reinterpret_cast<acc_t *>(ws + L.off_prow) : nullptr;
+    a.acc_g = reinterpret_cast<acc_t *>(ws + L.off_acc_g);
+    a.acc_l = P.row_loss_out ? reinterpret_cast<acc_t *>(ws + L.off_acc_l) : nullptr;
+    a.acc_s = want_signs ? reinterpret_cast<int *>(ws + L.off_acc_s) : nullptr;
     a.lossp = reinterpret_cast<acc_t *>(ws + L.off_lossp);
     a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
-
-    a.colpart = nullptr; a.Pinv = 0; a.B = P.B; a.max_segs = L.max_segs;
-    if (P.use_triangle && all_rows && n_rows > 0) return run_reg_tri_tail(P, L, a, perm, combo_cost, ws, st);
+    a.colpart = nullptr; a.Pinv = 0; a.B = P.B;
+    if (triangle) return run_reg_tri_tail(P, L, a, perm, combo_cost, ws, st);
 
     if (n_rows > 0) {
-        // slots of a (segment, half) that processed nothing of a row tile must read as zero
-        if (want_grad) ARVAE_CUDA_TRY(cudaMemsetAsync(a.pgrad, 0, L.slot_bytes, st));
-        if (a.prow) ARVAE_CUDA_TRY(cudaMemsetAsync(a.prow, 0, L.slot_bytes, st));
+        // the accumulators in use are contiguous: gradient [, loss [, signs]]
+        if (want_grad || a.acc_l || a.acc_s) {
+            const size_t first = want_grad ? L.off_acc_g : (a.acc_l ? L.off_acc_l : L.off_acc_s);
+            const size_t last = a.acc_s ? L.off_acc_s + sizeof(int) * (size_t)L.n_rr * kTileRows
+                                        : (a.acc_l ? L.off_acc_l + L.acc_bytes : L.off_acc_g + L.acc_bytes);
+            ARVAE_CUDA_TRY(cudaMemsetAsync(ws + first, 0, last - first, st));
+        }
         plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);
         ARVAE_LAUNCH_CHECK("plan_classes_kernel");
         plan_scan_kernel<<<1, 1024, 0, st>>>(combo_cost, L.n_rr, a.prefix);
         ARVAE_LAUNCH_CHECK("plan_scan_kernel");
         profile_begin(st);
-        if (want_grad) reg_tiles_kernel<true><<<a.G, kDuoThreads, kDuoStageBytes, st>>>(a);
-        else reg_tiles_kernel<false><<<a.G, kDuoThreads, kDuoStageBytes, st>>>(a);
+        launch_tiles(a, a.G, want_grad, want_signs, st);
         profile_end(st);
         ARVAE_LAUNCH_CHECK("reg_tiles_kernel");
-    } else {
-        a.G = 0;
     }
 
-    const double BB = (double)P.B * (double)P.B;
-    const double lscale = (double)P.gamma / BB;
-    const double gscale = 8.0 * (double)P.gamma * (double)P.factor / BB;
-    const double pad_per_row = (double)(L.Bpad - P.B);
+    double lscale, gscale, pad_per_row;
+    reg_scales(P, L.Bpad, lscale, gscale, pad_per_row);
     const int64_t work = n_rows * P.R;
     reg_tiles_epilogue_kernel<<<(unsigned)(work > 0 ? ceil_div(work, 256) : 1), 256, 0, st>>>(
-        a, perm, P.R, P.row_begin, gscale, lscale, pad_per_row, P.grad_cols_out, P.row_loss_out,
-        P.loss_out, P.loss_f32_out);
+        a, perm, P.R, P.row_begin, n_rows > 0 ? a.G : 0, gscale, lscale, pad_per_row, P.grad_cols_out, P.row_loss_out,
+        P.row_sign_out, P.loss_out, P.loss_f32_out);
     ARVAE_LAUNCH_CHECK("reg_tiles_epilogue_kernel");
     return 0;
 }
+
+#include "reg_shard.cuh"
 
 }  // namespace arvae

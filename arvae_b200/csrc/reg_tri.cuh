@@ -213,7 +213,7 @@ reg_tri_kernel(TilesArgs a) {
     __shared__ unsigned int scol[kStageCols * 2];  // fixed-point column sums of the current batch (<= 1024 * 2^20 = 2^30)
     __shared__ unsigned int swords[kStageSubs];
     __shared__ int sJ[kStageSubs];
-    __shared__ acc_t sred[kTileThreads / 32];
+    __shared__ acc_t sred[2][kTileThreads / 32];
     __shared__ int s_rng[4];
     __shared__ int s_scan[kTileThreads];
 
@@ -231,7 +231,7 @@ reg_tri_kernel(TilesArgs a) {
     int sp0 = s_rng[1];
     const int64_t rr_end = s_rng[2];
     const int sp_end = s_rng[3];
-    acc_t lthread = 0;
+    acc_t lhi = 0, llo = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     while (rr < rr_end || (rr == rr_end && sp0 < sp_end)) {
@@ -320,31 +320,31 @@ reg_tri_kernel(TilesArgs a) {
         __syncthreads();
         if (threadIdx.x < kStageSubs) swords[threadIdx.x] = 0u;
 
-        int64_t seg = c - owner_of_pos(a.prefix[rr], T, a.G);
-        if (seg >= a.max_segs) {
-            if (threadIdx.x == 0) atomicExch(const_cast<int *>(a.flags) + ARVAE_MAX_REG_DIMS, 1);
-            seg = a.max_segs - 1;
-        }
-        const int64_t slot = (seg * a.n_rr + rr) * kTileRows;
+        // this CTA's share of row tile rr goes to the fixed-point row accumulators (integer atomics: order-free)
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
-            const int64_t o = slot + warp * kWarpRowsT + k * 32 + lane;
-            if (valid[k]) lthread += dl[k] >> kLossShift;
-            if (GRAD) a.pgrad[o] = valid[k] ? dg[k] : 0;
-            if (a.prow) a.prow[o] = valid[k] ? dl[k] : 0;
+            const int64_t o = rr * kTileRows + warp * kWarpRowsT + k * 32 + lane;
+            if (valid[k]) {
+                lhi += dl[k] >> kLossSplitBits;
+                llo += dl[k] & kLossLoMask;
+                if (GRAD && dg[k] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.acc_g + o), (unsigned long long)dg[k]);
+                if (a.acc_l && dl[k] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(a.acc_l + o), (unsigned long long)dl[k]);
+            }
         }
         ++rr;
         sp0 = 0;
     }
 
-    lthread = warp_sum(lthread);
-    if (lane == 0) sred[warp] = lthread;
+    lhi = warp_sum(lhi);
+    llo = warp_sum(llo);
+    if (lane == 0) { sred[0][warp] = lhi; sred[1][warp] = llo; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        acc_t t = 0;
+        acc_t th = 0, tl = 0;
 #pragma unroll
-        for (int w = 0; w < kTileThreads / 32; ++w) t += sred[w];
-        a.lossp[c] = t;
+        for (int w = 0; w < kTileThreads / 32; ++w) { th += sred[0][w]; tl += sred[1][w]; }
+        a.lossp[2 * c] = th;
+        a.lossp[2 * c + 1] = tl;
         if (a.dbg_times) {
             unsigned long long tt;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
@@ -367,15 +367,7 @@ reg_tri_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, double
         const int64_t q = idx % a.n_rows;
         const int64_t Iq = q / kTileRows, lr = q % kTileRows;
         const int64_t rr = (int64_t)r * a.n_row_tiles + Iq;
-        const long long T = a.prefix[a.n_rr];
-        const int64_t c0 = owner_of_pos(a.prefix[rr], T, a.G);
-        const int64_t c1 = owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G);
-        const int64_t nseg = min(c1 - c0 + 1, (int64_t)a.max_segs);
-        acc_t gi = 0, li = 0;
-        for (int64_t seg = 0; seg < nseg; ++seg) {
-            if (grad_cols) gi += a.pgrad[(seg * a.n_rr + rr) * kTileRows + lr];
-            if (row_loss) li += a.prow[(seg * a.n_rr + rr) * kTileRows + lr];
-        }
+        const acc_t gi = grad_cols ? a.acc_g[rr * kTileRows + lr] : 0, li = row_loss ? a.acc_l[rr * kTileRows + lr] : 0;
         const double g = (double)gi * kFixScale, l = (double)li * kFixScale;
         // column side
         const int64_t J = q / kSubCols;
@@ -402,8 +394,10 @@ reg_tri_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, double
         }
         my_col_loss = cl;
         const int64_t out = (int64_t)perm[(int64_t)r * a.Bpad + q] * R + r;
-        if (grad_cols) grad_cols[out] = (float)((g + cg) * gscale);
-        if (row_loss) row_loss[out] = l + cl - pad_per_row;
+        const bool poisoned = row_is_poisoned(a.flags, r, a.Xs[(int64_t)r * a.Bpad + q]);
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        if (grad_cols) grad_cols[out] = poisoned ? (float)nan : (float)((g + cg) * gscale);
+        if (row_loss) row_loss[out] = poisoned ? nan : l + cl - pad_per_row;
     }
     my_col_loss = warp_sum(my_col_loss);
     if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = my_col_loss;
@@ -417,11 +411,13 @@ reg_tri_epilogue_kernel(TilesArgs a, const int *__restrict__ perm, int R, double
 
 __global__ void __launch_bounds__(256)
 reg_tri_finish_kernel(const acc_t *__restrict__ lossp, int64_t n_lossp, const double *__restrict__ eloss,
-                      int64_t n_eloss, double pad_total, double lscale, const int *__restrict__ overflow_flag,
+                      int64_t n_eloss, double pad_total, double lscale, const int *__restrict__ flags, int R,
                       double *__restrict__ loss_out, float *__restrict__ loss_f32_out) {
     __shared__ double sh[256];
-    double t = 0.0;
-    for (int64_t u = threadIdx.x; u < n_lossp; u += 256) t += (double)lossp[u] * kLossScale;
+    __shared__ acc_t shl[512];
+    acc_t hi, lo;
+    sum_loss_partials(lossp, n_lossp, shl, hi, lo);
+    double t = threadIdx.x == 0 ? loss_from_hilo(hi, lo) : 0.0;
     for (int64_t u = threadIdx.x; u < n_eloss; u += 256) t += eloss[u];
     sh[threadIdx.x] = t;
     __syncthreads();
@@ -431,7 +427,7 @@ reg_tri_finish_kernel(const acc_t *__restrict__ lossp, int64_t n_lossp, const do
     }
     if (threadIdx.x == 0) {
         double total = (sh[0] - pad_total) * lscale;
-        if (overflow_flag && *overflow_flag) total = __longlong_as_double(0x7ff8000000000000LL);
+        if (any_nonfinite(flags, R)) total = __longlong_as_double(0x7ff8000000000000LL);
         *loss_out = total;
         if (loss_f32_out) *loss_f32_out = (float)total;
     }
@@ -472,7 +468,6 @@ static int run_reg_tri_tail(const RegProblem &P, const SortedLayout &L, TilesArg
     a.colpart = reinterpret_cast<float2 *>(ws + L.off_colpart);
     a.Pinv = mod_inverse(a.P, a.S);
     a.B = P.B;
-    a.max_segs = L.max_segs;
     int64_t G = (int64_t)sm_count() * tri_ctas_per_sm(want_grad);
     if (G > L.G_max) G = L.G_max;
     if (G < 1) G = 1;
@@ -481,9 +476,8 @@ static int run_reg_tri_tail(const RegProblem &P, const SortedLayout &L, TilesArg
     const int64_t work = P.B * P.R;
     const int64_t n_eblocks = work > 0 ? ceil_div(work, 256) : 1;
 
-    // slots of CTAs that own no unit of a row tile must read as zero
-    ARVAE_CUDA_TRY(cudaMemsetAsync(a.pgrad, 0, L.slot_bytes, st));
-    if (a.prow) ARVAE_CUDA_TRY(cudaMemsetAsync(a.prow, 0, L.slot_bytes, st));
+    ARVAE_CUDA_TRY(cudaMemsetAsync(a.acc_g, 0, L.acc_bytes, st));
+    if (a.acc_l) ARVAE_CUDA_TRY(cudaMemsetAsync(a.acc_l, 0, L.acc_bytes, st));
     tri_plan_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);
     ARVAE_LAUNCH_CHECK("tri_plan_kernel");
     plan_scan_kernel<<<1, 1024, 0, st>>>(combo_cost, L.n_rr, a.prefix);
@@ -494,15 +488,13 @@ static int run_reg_tri_tail(const RegProblem &P, const SortedLayout &L, TilesArg
     profile_end(st);
     ARVAE_LAUNCH_CHECK("reg_tri_kernel");
 
-    const double BB = (double)P.B * (double)P.B;
-    const double lscale = (double)P.gamma / BB;
-    const double gscale = 8.0 * (double)P.gamma * (double)P.factor / BB;
-    const double pad_per_row = (double)(L.Bpad - P.B);
+    double lscale, gscale, pad_per_row;
+    reg_scales(P, L.Bpad, lscale, gscale, pad_per_row);
     reg_tri_epilogue_kernel<<<(unsigned)n_eblocks, 256, 0, st>>>(a, perm, P.R, gscale, pad_per_row, P.grad_cols_out,
                                                                P.row_loss_out, eloss);
     ARVAE_LAUNCH_CHECK("reg_tri_epilogue_kernel");
     reg_tri_finish_kernel<<<1, 256, 0, st>>>(a.lossp, a.G, eloss, n_eblocks, pad_per_row * (double)P.B * (double)P.R,
-                                             lscale, a.flags + ARVAE_MAX_REG_DIMS, P.loss_out, P.loss_f32_out);
+                                             lscale, a.flags, P.R, P.loss_out, P.loss_f32_out);
     ARVAE_LAUNCH_CHECK("reg_tri_finish_kernel");
     return 0;
 }

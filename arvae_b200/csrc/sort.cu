@@ -27,18 +27,19 @@ __device__ __forceinline__ unsigned int float_to_sortable(float a) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__global__ void __launch_bounds__(256)
-make_keys_kernel(const float *__restrict__ lab, int64_t lrs, int64_t lcs, RegDims dims, int64_t B,
-                 int64_t N, unsigned long long *__restrict__ keys) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (j >= N) return;
-    unsigned long long k = ~0ull;  // padding sorts last
-    if (j < B) {
-        const float a = __ldg(lab + j * lrs + (int64_t)dims.lcol[r] * lcs);
-        k = ((unsigned long long)float_to_sortable(a) << 32) | (unsigned long long)(unsigned int)j;
-    }
-    keys[(int64_t)r * N + j] = k;
+// Key of sample j (local index) of dim r.
+//   plain     (spec.z == null):  [sortable attribute : 32][index : 32]
+//   segmented (spec.z != null):  [outlier : 1][sortable attribute : 32][index + idx_offset : 31]
+// "outlier" = the factorised one-MUFU tanh cannot be used for this element (|2 f log2(e) z| > 62, NaN or inf): such
+// elements sort into their own attribute-ordered segment after all inliers, so that the pair kernel can pick the tanh
+// form per tile (reg_sorted.cu).  Padding (~0) sorts last in both formats.
+__device__ __forceinline__ unsigned long long make_sort_key(const KeySpec &s, int r, int64_t j) {
+    const float a = __ldg(s.lab + j * s.lrs + (int64_t)s.dims.lcol[r] * s.lcs);
+    const unsigned long long sa = float_to_sortable(a);
+    if (!s.z) return (sa << 32) | (unsigned long long)(unsigned int)j;
+    const float u = s.cabs * signed_latent(__ldg(s.z + j * s.zrs + (int64_t)s.dims.zcol[r] * s.zcs), s.fsign);
+    const unsigned long long out = (!s.segment || fabsf(u) <= kMufu1MaxAbsU) ? 0ull : 1ull;  // NaN / inf: outlier
+    return (out << 63) | (sa << 31) | (unsigned long long)(j + s.idx_offset);
 }
 
 __device__ __forceinline__ void cmpx(unsigned long long &a, unsigned long long &b, bool asc) {
@@ -136,24 +137,19 @@ __device__ __forceinline__ void smem_steps_down_to_256(unsigned long long *s, in
 
 // Sorts each kSortChunk-sized chunk in shared memory: all stages with k <= kSortChunk when
 // `k_only` == 0, or only the tail j = kSortChunk/2 .. 1 of stage `k_only` when merging.
-// With `lab` != null (first pass, k_only == 0) the keys are built on the fly from the label column instead of
-// being read back (saves the make_keys launch and a round trip through memory).
+// With `build` (first pass, k_only == 0) the keys are built on the fly from the label (and latent) column instead
+// of being read back (saves a launch and a round trip through memory).
 __global__ void __launch_bounds__(kSortThreads)
-bitonic_local_kernel(unsigned long long *__restrict__ keys, int64_t N, int64_t k_only,
-                     const float *__restrict__ lab, int64_t lrs, int64_t lcs, RegDims dims, int64_t B) {
+bitonic_local_kernel(unsigned long long *__restrict__ keys, int64_t N, int64_t k_only, int build, KeySpec spec,
+                     int64_t B) {
     extern __shared__ __align__(16) unsigned long long s[];
     unsigned long long *base = keys + (int64_t)blockIdx.y * N + (int64_t)blockIdx.x * kSortChunk;
     const int64_t g0 = (int64_t)blockIdx.x * kSortChunk;  // global index of s[0] within this dim
     const int n = (int)min((int64_t)kSortChunk, N);       // N is a power of two >= 256
-    if (lab) {
+    if (build) {
         for (int i = threadIdx.x; i < n; i += kSortThreads) {
             const int64_t j = g0 + i;
-            unsigned long long k = ~0ull;  // padding sorts last
-            if (j < B) {
-                const float a = __ldg(lab + j * lrs + (int64_t)dims.lcol[blockIdx.y] * lcs);
-                k = ((unsigned long long)float_to_sortable(a) << 32) | (unsigned long long)(unsigned int)j;
-            }
-            s[i] = k;
+            s[i] = j < B ? make_sort_key(spec, blockIdx.y, j) : ~0ull;  // padding sorts last
         }
     } else {
         for (int i = threadIdx.x; i < n; i += kSortThreads) s[i] = base[i];
@@ -227,8 +223,7 @@ __device__ __forceinline__ void coop_global_round(unsigned long long *__restrict
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-bitonic_coop_kernel(unsigned long long *__restrict__ keys, int64_t N, const float *__restrict__ lab, int64_t lrs,
-                    int64_t lcs, RegDims dims, int64_t B) {
+bitonic_coop_kernel(unsigned long long *__restrict__ keys, int64_t N, KeySpec spec, int64_t B) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned long long s[];
     unsigned long long *dim_base = keys + (int64_t)blockIdx.y * N;
@@ -237,12 +232,7 @@ bitonic_coop_kernel(unsigned long long *__restrict__ keys, int64_t N, const floa
     const int n = (int)min((int64_t)kSortChunk, N);
     for (int i = threadIdx.x; i < n; i += kSortThreads) {
         const int64_t j = g0 + i;
-        unsigned long long k = ~0ull;  // padding sorts last
-        if (j < B) {
-            const float a = __ldg(lab + j * lrs + (int64_t)dims.lcol[blockIdx.y] * lcs);
-            k = ((unsigned long long)float_to_sortable(a) << 32) | (unsigned long long)(unsigned int)j;
-        }
-        s[i] = k;
+        s[i] = j < B ? make_sort_key(spec, blockIdx.y, j) : ~0ull;  // padding sorts last
     }
     __syncthreads();
     smem_round_tail(s, n, g0, 2, min(256, n));
@@ -318,13 +308,22 @@ static void launch_global(unsigned long long *keys, int64_t N, int R, int64_t k,
 // keys[r][0..N) <- sorted (ascending) attribute keys of dim r; N = sort_padded_size(B).
 int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, int64_t B,
                   int64_t N, unsigned long long *keys, cudaStream_t st) {
+    KeySpec spec;
+    spec.lab = lab; spec.lrs = lrs; spec.lcs = lcs;
+    spec.z = nullptr; spec.zrs = spec.zcs = 0;
+    spec.fsign = 1.0f; spec.cabs = 1.0f; spec.idx_offset = 0; spec.segment = 0;
+    spec.dims = dims;
+    return run_sort_keys_spec(spec, R, B, N, keys, st);
+}
+
+int run_sort_keys_spec(const KeySpec &spec, int R, int64_t B, int64_t N, unsigned long long *keys, cudaStream_t st) {
     static_assert(kSortChunk * sizeof(unsigned long long) <= 48 * 1024, "fits the default dynamic shared memory limit");
     const int64_t chunks = N > kSortChunk ? N / kSortChunk : 1;
     const size_t smem = (size_t)(N < kSortChunk ? N : kSortChunk) * sizeof(unsigned long long);
     dim3 gl((unsigned)chunks, (unsigned)R);
     if (chunks > 1 && coop_sort_possible(chunks, R, smem, st)) {
-        RegDims d = dims;
-        void *args[] = {(void *)&keys, (void *)&N, (void *)&lab, (void *)&lrs, (void *)&lcs, (void *)&d, (void *)&B};
+        KeySpec sp = spec;
+        void *args[] = {(void *)&keys, (void *)&N, (void *)&sp, (void *)&B};
         cudaError_t e = cudaLaunchCooperativeKernel((const void *)bitonic_coop_kernel, gl, dim3(kSortThreads), args, smem, st);
         if (e == cudaSuccess) {
             count_launch();
@@ -332,7 +331,7 @@ int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dim
         }
         (void)cudaGetLastError();  // e.g. co-residency not available right now: fall through to the plain path
     }
-    bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, 0, lab, lrs, lcs, dims, B);
+    bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, 0, 1, spec, B);
     ARVAE_LAUNCH_CHECK("bitonic_local_kernel");
     for (int64_t k = 2 * (int64_t)kSortChunk; k <= N; k <<= 1) {
         int64_t j = k >> 1;
@@ -345,7 +344,7 @@ int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dim
             ARVAE_LAUNCH_CHECK("bitonic_global_kernel");
             j >>= steps;
         }
-        bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, k, nullptr, 0, 0, dims, B);
+        bitonic_local_kernel<<<gl, kSortThreads, smem, st>>>(keys, N, k, 0, spec, B);
         ARVAE_LAUNCH_CHECK("bitonic_local_kernel(merge)");
     }
     return 0;

@@ -106,8 +106,9 @@ def _prepare_labels(labels: torch.Tensor, label_cols: Sequence[int], B: int, dev
 
 def _launch_reg(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], label_cols: Sequence[int],
                 gamma: float, factor: float, row_begin: int, row_end: int, want_grad: bool, algo: int,
-                want_row_loss: bool = False):
-    """One call of arvae_reg_loss_fwdbwd_f32. Returns (loss64[()] , loss32[()], grad_cols|None, row_loss|None)."""
+                want_row_loss: bool = False, want_row_sign: bool = False):
+    """One call of arvae_reg_loss_fwdbwd_f32. Returns (loss64[()] , loss32[()], grad_cols|None, row_loss|None)
+    (+ row_sign [rows, R] int32 as a fifth element when ``want_row_sign``)."""
     lib = _lib.load()
     dev = z.device
     B = z.shape[0]
@@ -118,14 +119,17 @@ def _launch_reg(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], 
         loss32 = torch.empty((), dtype=torch.float32, device=dev)
         grad_cols = torch.empty((n_rows, R), dtype=torch.float32, device=dev) if want_grad else None
         row_loss = torch.empty((n_rows, R), dtype=torch.float64, device=dev) if want_row_loss else None
+        row_sign = torch.empty((n_rows, R), dtype=torch.int32, device=dev) if want_row_sign else None
         ws_bytes = int(lib.arvae_reg_loss_workspace_bytes_algo(B, n_rows, R, algo))
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         rc = lib.arvae_reg_loss_fwdbwd_f32(
             _ptr(z), z.stride(0), z.stride(1), _ptr(labels), labels.stride(0), labels.stride(1),
             _lib.i32_array(reg_dims), _lib.i32_array(label_cols), R, row_begin, row_end, B,
-            gamma, factor, algo, _ptr(loss64), _ptr(loss32), _ptr(grad_cols), _ptr(row_loss),
+            gamma, factor, algo, _ptr(loss64), _ptr(loss32), _ptr(grad_cols), _ptr(row_loss), _ptr(row_sign),
             _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(rc, "arvae_reg_loss_fwdbwd_f32")
+    if want_row_sign:
+        return loss64, loss32, grad_cols, row_loss, row_sign
     return loss64, loss32, grad_cols, row_loss
 
 
@@ -243,23 +247,31 @@ def reg_loss_sign(latent_code: torch.Tensor, attribute: torch.Tensor, factor=1.0
 
 
 def reg_loss_rows(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], gamma, factor, row_begin: int,
-                  row_end: int, want_grad: bool = True, algo: int = ALGO_AUTO, want_row_loss: bool = False):
+                  row_end: int, want_grad: bool = True, algo: int = ALGO_AUTO, want_row_loss: bool = False,
+                  want_row_sign: bool = False):
     """Row-block form (no autograd): the block's share of the loss as a 0-d float64 tensor, the
-    gradient columns [rows, R] and optionally the per-row loss sums [rows, R]."""
+    gradient columns [rows, R] and optionally the per-row loss sums [rows, R].
+
+    ``want_row_sign`` appends a fourth result: int32 [rows, R] = sum_j sign(a_i - a_j) as accumulated by the PAIR
+    KERNEL itself from the tile classes / compares it evaluated the loss with -- the integer check of the
+    attribute sign matrix through the hot path (reference utils/trainer.py:394-395, 400)."""
     _require_cuda_f32(z, "z")
     dims = _normalize_dims(reg_dims, z.shape[1])
     lab, lcols = _prepare_labels(labels, dims, z.shape[0], z.device)
-    loss64, _, grad_cols, row_loss = _launch_reg(z.detach(), lab, dims, lcols, _scalar(gamma), _scalar(factor),
-                                                 int(row_begin), int(row_end), want_grad, int(algo),
-                                                 want_row_loss)
-    return loss64, grad_cols, row_loss
+    out = _launch_reg(z.detach(), lab, dims, lcols, _scalar(gamma), _scalar(factor), int(row_begin), int(row_end),
+                      want_grad, int(algo), want_row_loss, want_row_sign)
+    if want_row_sign:
+        return out[0], out[2], out[3], out[4]
+    return out[0], out[2], out[3]
 
 
 def mufu_per_pair(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int], gamma, factor,
                   algo: int = ALGO_AUTO) -> Tuple[float, ...]:
-    """MUFU instructions per evaluated pair, per regularised dim, that the kernels use on these inputs:
-    1 when the attribute-sorted path runs the factorised tanh (range guard |2 f log2(e) z| <= 62 holds
-    for the whole column), else 2.  Runs one forward to find out (roofline bookkeeping for bench.py)."""
+    """MUFU instructions per evaluated pair, per regularised dim, that the kernels use on these inputs.  The
+    attribute-sorted path keeps the samples with |2 f log2(e) z| <= 62 ("inliers") in a segment of their own: pairs of
+    two inliers take the factorised one-MUFU tanh, pairs with an outlier the two-MUFU form, so a dim with n_in
+    inliers costs 2 - (n_in / B)^2 MUFU per pair (tiles straddling the segment boundary aside).  The dense path is
+    always 2.  Runs one forward to find out (roofline bookkeeping for bench.py)."""
     _require_cuda_f32(z, "z")
     dims = _normalize_dims(reg_dims, z.shape[1])
     lab, lcols = _prepare_labels(labels, dims, z.shape[0], z.device)
@@ -270,14 +282,14 @@ def mufu_per_pair(z: torch.Tensor, labels: torch.Tensor, reg_dims: Sequence[int]
         ws = torch.empty(max(int(lib.arvae_reg_loss_workspace_bytes_algo(B, B, R, int(algo))), 256), dtype=torch.uint8, device=z.device)
         rc = lib.arvae_reg_loss_fwdbwd_f32(_ptr(z), z.stride(0), z.stride(1), _ptr(lab), lab.stride(0), lab.stride(1),
                                            _lib.i32_array(dims), _lib.i32_array(lcols), R, 0, B, B, _scalar(gamma),
-                                           _scalar(factor), int(algo), _ptr(loss64), None, None, None, _ptr(ws),
+                                           _scalar(factor), int(algo), _ptr(loss64), None, None, None, None, _ptr(ws),
                                            ws.numel(), _stream(z.device))
         _lib.check(rc, "arvae_reg_loss_fwdbwd_f32")
-        flags = (ctypes.c_int32 * R)()
-        rc = lib.arvae_reg_loss_path_flags(B, B, R, int(algo), _ptr(ws), flags, _stream(z.device))
+        n_in = (ctypes.c_int32 * R)()
+        rc = lib.arvae_reg_loss_path_flags(B, B, R, int(algo), _ptr(ws), n_in, _stream(z.device))
         if rc != 0:
             return tuple(2.0 for _ in range(R))
-    return tuple(2.0 if f else 1.0 for f in flags)
+    return tuple(2.0 - (float(n) / max(B, 1)) ** 2 for n in n_in)
 
 
 def attr_argsort(attribute: torch.Tensor) -> torch.Tensor:

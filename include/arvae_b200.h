@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define ARVAE_VERSION 100
+#define ARVAE_VERSION 200
 
 #if defined(__GNUC__)
 #define ARVAE_API __attribute__((visibility("default")))
@@ -88,6 +88,10 @@ ARVAE_API size_t arvae_reg_loss_workspace_bytes_algo(int64_t B_total, int64_t n_
  *                  gradient of the mean loss, times gamma), NULL skips the gradient math
  *   row_loss_out_dev  [n_rows, R] double or NULL: per-row unnormalised sums  sum_j |t_ij - s_ij|
  *                  (parity/debug output)
+ *   row_sign_out_dev  [n_rows, R] int32 or NULL: sum_j sign(a[i,c_r] - a[j,c_r]) accumulated by the PAIR KERNEL from
+ *                  the very classification / compares it evaluated the loss with (reference utils/trainer.py:394-395,
+ *                  400) -- the integer check that the attribute sign matrix of the hot path is bit-exact.  Needs
+ *                  grad_cols_out_dev; not offered by ARVAE_ALGO_TRIANGLE.
  */
 ARVAE_API int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t z_col_stride,
                               const float *labels_dev, int64_t lab_row_stride,
@@ -95,14 +99,15 @@ ARVAE_API int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride
                               const int32_t *label_cols_host, int32_t R, int64_t row_begin,
                               int64_t row_end, int64_t B_total, float gamma, float factor,
                               int32_t algo, double *loss_out_dev, float *loss_f32_out_dev,
-                              float *grad_cols_out_dev, double *row_loss_out_dev,
+                              float *grad_cols_out_dev, double *row_loss_out_dev, int32_t *row_sign_out_dev,
                               void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /*
- * Which tanh form the attribute-sorted path used per dim in the call that last wrote `workspace_dev`
- * (same B_total / n_rows / R): flags_out_host[r] = 0 -> 1 MUFU per pair (factorised E_j/(E_i+E_j)),
- * 1 -> 2 MUFU per pair (range guard tripped: some |2 f log2(e) x| > 62).  Synchronises `stream`.
- * Returns ARVAE_E_BADARG when the shape selects the dense path under `algo` (always 2 MUFU per pair).
+ * Which tanh form the attribute-sorted path used in the call that last wrote `workspace_dev` (same B_total / n_rows /
+ * R): flags_out_host[r] = number of INLIER samples of dim r, i.e. samples with |2 f log2(e) x| <= 62.  Pairs of two
+ * inliers cost one MUFU (factorised E_j/(E_i+E_j)), pairs with an outlier two (EX2 + RCP on the latent difference):
+ * the MUFU count per pair of dim r is 2 - (n_in/B)^2 up to the few tiles that straddle the segment boundary.
+ * Synchronises `stream`.  Returns ARVAE_E_BADARG when the shape selects the dense path (always 2 MUFU per pair).
  */
 ARVAE_API int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_t algo,
                                         const void *workspace_dev, int32_t *flags_out_host,
@@ -174,6 +179,50 @@ ARVAE_API int arvae_pack_columns_f32(const float *z_dev, int64_t z_row_stride, i
                                      int64_t lab_col_stride, const int32_t *reg_dims_host,
                                      const int32_t *label_cols_host, int32_t R, int64_t n_rows,
                                      float *out_dev, void *stream);
+
+
+/*
+ * The same step sharded over the GPUs of one NVSwitch box, one process per GPU, with the exchange done by the kernels
+ * themselves over NVLink peer memory (csrc/reg_shard.cuh; BASELINE.json north_star's multi-GPU path):
+ * every rank argsorts its own rows and stores the sorted run into every peer's buffer (the column all-gather), the
+ * runs are merged into the single-GPU sorted order, each rank sweeps its 1/world share of that order's row blocks,
+ * then pulls the row sums of its own samples and every rank's loss partial from the peers (gradient return +
+ * all-reduce).  Loss and gradients are BITWISE those of arvae_reg_loss_fwdbwd_f32 on the concatenated batch.
+ *
+ *   arvae_shard_create        allocates this rank's communication buffer and workspace for up to n_cap rows per
+ *                             rank and R_cap regularised dims (world <= 16)
+ *   arvae_shard_ipc_handle    64-byte CUDA IPC handle of the communication buffer, to be all-gathered by the caller
+ *                             (torch.distributed / MPI / a pipe: plumbing, done once)
+ *   arvae_shard_open_peers    maps every peer's buffer from the gathered handles [world][64]
+ *   arvae_shard_set_peer      alternative for peers that live in the same process or are mapped by other means
+ *   arvae_shard_reg_loss_f32  one step.  z_local_dev / labels_local_dev hold THIS rank's n_all_host[rank] rows;
+ *                             loss_out_dev [1] double (+ optional float) receives the GLOBAL loss on every rank,
+ *                             grad_cols_out_dev [n_local, R] the gradient columns of this rank's rows (NULL: loss only).
+ *                             `phases` = 0 runs the whole step; bits 1 | 2 | 4 run only publish / merge+pairs /
+ *                             finalize (tests drive several ranks of one process through the phases in lockstep).
+ *                             Stream-ordered, no host sync, no NCCL.  A peer that never shows up makes the loss NaN
+ *                             after a bounded wait (arvae_shard_status reports it) instead of hanging the GPU.
+ *   arvae_shard_reg_loss_host_f32  the same with HOST buffers in and out (H2D, step, dL/dz scatter, D2H, sync).
+ */
+#define ARVAE_SHARD_HANDLE_BYTES 64
+ARVAE_API size_t arvae_shard_comm_bytes(int64_t n_cap, int32_t R_cap, int32_t world);
+ARVAE_API int arvae_shard_create(int32_t rank, int32_t world, int64_t n_cap, int32_t R_cap, void **ctx_out);
+ARVAE_API int arvae_shard_ipc_handle(void *ctx, void *handle_out);
+ARVAE_API int arvae_shard_open_peers(void *ctx, const void *handles);
+ARVAE_API int arvae_shard_set_peer(void *ctx, int32_t rank, void *comm_dev);
+ARVAE_API void *arvae_shard_comm_ptr(void *ctx);
+ARVAE_API int arvae_shard_reg_loss_f32(void *ctx, const float *z_local_dev, int64_t z_row_stride, int64_t z_col_stride,
+                                       const float *labels_local_dev, int64_t lab_row_stride, int64_t lab_col_stride,
+                                       const int32_t *reg_dims_host, const int32_t *label_cols_host, int32_t R,
+                                       const int64_t *n_all_host, float gamma, float factor, double *loss_out_dev,
+                                       float *loss_f32_out_dev, float *grad_cols_out_dev, int32_t phases, void *stream);
+ARVAE_API int arvae_shard_reg_loss_host_f32(void *ctx, const float *z_local_host, int64_t Z,
+                                            const float *labels_local_host, int64_t A, const int32_t *reg_dims_host,
+                                            const int32_t *label_cols_host, int32_t R, const int64_t *n_all_host,
+                                            float gamma, float factor, float *loss_out_host, float *grad_z_out_host,
+                                            void *stream);
+ARVAE_API int arvae_shard_status(void *ctx, int32_t *status_out, uint64_t *epoch_out, void *stream);
+ARVAE_API int arvae_shard_destroy(void *ctx);
 
 /*
  * perm_out_dev[k] = index of the k-th smallest attribute (ties by index, NaN last): the order the

@@ -34,22 +34,28 @@ def test_header_symbols_all_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.arvae_version() == 100
+    assert lib.arvae_version() == 200
     assert isinstance(lib.arvae_last_error(), bytes)
 
 
 def test_argument_errors_need_no_gpu(lib):
     dims = (ctypes.c_int32 * 2)(0, 1)
     rc = lib.arvae_reg_loss_fwdbwd_f32(None, 1, 1, None, 1, 1, dims, dims, 99, 0, 4, 4, 1.0, 1.0, 0,
-                                       None, None, None, None, None, 0, None)
+                                       None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"out of range" in lib.arvae_last_error()
     rc = lib.arvae_reg_loss_fwdbwd_f32(None, 1, 1, None, 1, 1, dims, dims, 2, 3, 2, 4, 1.0, 1.0, 0,
-                                       None, None, None, None, None, 0, None)
+                                       None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"row range" in lib.arvae_last_error()
     neg = (ctypes.c_int32 * 1)(-1)
     rc = lib.arvae_reg_loss_scatter_bwd_f32(None, None, neg, 1, 0, 4, None, 4, None)
     assert rc == -1 and b"negative" in lib.arvae_last_error()
     assert lib.arvae_reg_loss_workspace_bytes(-1, 0, 1) == 0
+    # sharded step: argument checks come before any CUDA call
+    ctx = ctypes.c_void_p()
+    assert lib.arvae_shard_create(3, 2, 128, 4, ctypes.byref(ctx)) == -1   # rank >= world
+    assert lib.arvae_shard_create(0, 17, 128, 4, ctypes.byref(ctx)) == -1  # more ranks than one NVSwitch box
+    assert lib.arvae_shard_comm_bytes(0, 4, 2) == 0
+    assert lib.arvae_shard_comm_bytes(8192, 6, 8) > 8 * 6 * 8192 * 12
 
 
 def test_python_layer_refuses_cpu_tensors():

@@ -50,9 +50,18 @@ def _worker(rank, world, port, q):
         lab_local = c["labels"][rank * n:(rank + 1) * n].clone()
         # bypass the CUDA-only dtype/device guard of the public wrapper: call the autograd node directly
         dims = tuple(c["reg_dims"])
-        loss = adist._ShardedRegLossFn.apply(z_local, lab_local, dims, dims, c["gamma"], c["delta"], None, 0)
+        loss = adist._ShardedRegLossFn.apply(z_local, lab_local, dims, dims, c["gamma"], c["delta"], None, 0, None, 1.0)
         (loss * 3.0).backward()
-        q.put((rank, float(loss), z_local.grad.numpy()))
+        # the same step under DistributedDataParallel with ddp_average (grad_scale = world): the rank-averaged
+        # parameter gradient must be the single-process global-batch one
+        torch.manual_seed(7)
+        enc = torch.nn.Linear(6, c["z"].shape[1], bias=False)
+        ddp = torch.nn.parallel.DistributedDataParallel(enc)
+        x_all = torch.randn(c["B"], 6, generator=torch.Generator().manual_seed(11))
+        z2 = ddp(x_all[rank * n:(rank + 1) * n])
+        loss2 = adist._ShardedRegLossFn.apply(z2, lab_local, dims, dims, c["gamma"], c["delta"], None, 0, None, float(world))
+        loss2.backward()
+        q.put((rank, float(loss), z_local.grad.numpy(), float(loss2), enc.weight.grad.numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -80,6 +89,18 @@ def test_two_rank_sharding_reproduces_single_rank_result(oracle_mod):
     # each rank's gradient rows are its block of the single-rank gradient (times the upstream 3.0)
     got = np.concatenate([r[2] for r in results], axis=0)
     assert np.allclose(got, 3.0 * ref_grad.astype(np.float32), rtol=1e-6, atol=1e-9)
+    # DDP + ddp_average: W.grad (averaged over ranks by DDP) == x^T dL/dz of the global batch on one process
+    torch.manual_seed(7)
+    enc = torch.nn.Linear(6, c["z"].shape[1], bias=False)
+    x_all = torch.randn(c["B"], 6, generator=torch.Generator().manual_seed(11))
+    z_all = enc(x_all).detach()
+    l2, g2 = oracle_mod.compute_reg_loss_multi(z_all.numpy(), c["labels"].numpy(), c["reg_dims"], c["gamma"], c["delta"],
+                                               f64=True)
+    w_ref = g2.T @ x_all.numpy().astype(np.float64)
+    for r in results:
+        assert abs(r[3] - l2) <= 1e-6 * abs(l2)
+        assert np.allclose(r[4], w_ref, rtol=2e-5, atol=1e-7 * np.abs(w_ref).max())
+    assert np.array_equal(results[0][4], results[1][4])
 
 
 def test_pack_columns_layout():

@@ -127,6 +127,61 @@ def test_sign_matrix_bit_exact_on_dataset_like_labels(ab, oracle_mod):
         assert np.array_equal(got, oracle_mod.sign_matrix(lab.numpy()))
 
 
+def _sign_row_sums_numpy(a):
+    """sum_j sign(a_i - a_j) in O(B log B): (# a_j < a_i) - (# a_j > a_i); NaN compares false both ways."""
+    a = np.asarray(a, dtype=np.float32)
+    valid = np.sort(a[~np.isnan(a)])
+    out = np.zeros(a.shape[0], dtype=np.int64)
+    ok = ~np.isnan(a)
+    out[ok] = np.searchsorted(valid, a[ok], "left") - (valid.size - np.searchsorted(valid, a[ok], "right"))
+    return out
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+def test_hot_path_sign_sums_bit_exact_all_rows(ab, oracle_mod, algo):
+    """The integer check of the attribute sign matrix THROUGH the pair kernels: every row's sum_j sign(a_i - a_j),
+    accumulated by the dense loop's compares / the sorted kernel's tile classes while they evaluate the loss, equals
+    the row sums of the oracle's sign matrix (reference utils/trainer.py:394-395,400) exactly -- on tie-heavy
+    dSprites grids, NaN / +-inf / +-0 / subnormal labels, and with an outlier segment in the sorted order."""
+    from arvae_b200 import synth
+    B = 4096
+    lab = synth.make_labels("dsprites", B, 11)[:, 1:6].contiguous()
+    g = golden("sign_matrix_special")
+    special = torch.from_numpy(np.resize(g["a"], B).astype(np.float32))
+    special[torch.randperm(B, generator=torch.Generator().manual_seed(1))[:B // 2]] = 0.25
+    lab = torch.cat([lab, special[:, None], synth.make_labels("morpho", B, 5)[:, 4:5]], dim=1).contiguous()
+    R = lab.shape[1]
+    z = torch.randn(B, R, generator=torch.Generator().manual_seed(2))
+    z[::97, 3] = 30.0   # outliers of the factorised tanh: their own segment of the sorted order
+    _, grad_cols, _, row_sign = ab.reg_loss_rows(z.cuda(), lab.cuda(), tuple(range(R)), 1.0, 1.0, 0, B, algo=algo,
+                                                 want_row_sign=True)
+    got = row_sign.cpu().numpy()
+    for r in range(R):
+        a = lab[:, r].numpy()
+        assert np.array_equal(got[:, r], _sign_row_sums_numpy(a)), r
+    s_full = oracle_mod.sign_matrix(lab[:, R - 2].numpy()).astype(np.int64).sum(axis=1)  # the special-value column
+    assert np.array_equal(got[:, R - 2], s_full)
+    # row blocks (the NCCL sharding unit) give the same integers
+    _, _, _, part = ab.reg_loss_rows(z.cuda(), lab.cuda(), tuple(range(R)), 1.0, 1.0, 1000, 3000, algo=algo,
+                                     want_row_sign=True)
+    assert np.array_equal(part.cpu().numpy(), got[1000:3000])
+
+
+def test_hot_path_sign_sums_bit_exact_full_size(ab):
+    """Same integers at the full C4 size (B = 65 536, R = 6), where no dense sign matrix fits: every row."""
+    from arvae_b200 import synth
+    c = synth.make_case("c4_mnist_b65536")
+    lab = c["labels"].clone()
+    lab[:, 2] = torch.round(lab[:, 2])          # a tie-heavy column
+    lab[123, 3] = float("nan"); lab[60000, 3] = float("nan"); lab[7, 4] = float("inf")
+    B = c["B"]
+    _, _, _, row_sign = ab.reg_loss_rows(c["z"].cuda(), lab.cuda(), c["reg_dims"], c["gamma"], c["delta"], 0, B,
+                                         want_row_sign=True)
+    got = row_sign.cpu().numpy()
+    for r, dim in enumerate(c["reg_dims"]):
+        assert np.array_equal(got[:, r], _sign_row_sums_numpy(lab[:, dim].numpy())), dim
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases the reference handles
 # ------------------------------------------------------------------------------------------------
@@ -433,24 +488,57 @@ def test_pack_columns(ab):
     assert torch.equal(ab.pack_columns(zt, lab, (2,), (1,)), torch.cat([zt[:, [2]], lab[:, [1]]], dim=1))
 
 
-def test_mufu_range_guard_falls_back_to_two_mufu_form(ab, oracle_mod):
-    """|2 f log2(e) z| > 62 somewhere in a column -> that dim uses EX2+RCP on the latent difference; results
-    must still match the oracle, and the dims inside the guard keep the 1-MUFU form."""
+def test_outliers_of_the_one_mufu_form_get_their_own_segment(ab, oracle_mod):
+    """|2 f log2(e) z| > 62 for a sample -> it sorts into the dim's outlier segment and only ITS pairs use EX2+RCP on
+    the latent difference; a single outlier no longer sends the whole dim to two MUFU.  Results match the oracle."""
     B = 9000
     g = torch.Generator().manual_seed(9)
     z = torch.randn(B, 3, generator=g)
     z[5, 1] = 30.0           # 2.885 * 30 > 62
     labels = torch.randn(B, 3, generator=g)
     per_dim = ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 1, 2), 1.0, 1.0)
-    assert per_dim == (1.0, 2.0, 1.0)
+    assert per_dim[0] == 1.0 and per_dim[2] == 1.0
+    assert abs(per_dim[1] - (2.0 - ((B - 1) / B) ** 2)) < 1e-12
     ref_loss, ref_grad = oracle_mod.compute_reg_loss_multi(z.numpy(), labels.numpy(), (0, 1, 2), 1.0, 1.0, f64=True)
     zc = z.cuda().requires_grad_(True)
     loss = ab.reg_loss_fused(zc, labels.cuda(), (0, 1, 2), 1.0, 1.0)
     loss.backward()
     assert_loss_close(loss.item(), ref_loss)
     assert_grad_close(zc.grad.cpu().numpy(), ref_grad)
-    # delta = 10 (the MeasureVAE setting): every N(0,1) column trips the guard
-    assert set(ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 2), 1.0, 10.0)) == {2.0}
+    # delta = 10 (the MeasureVAE setting, train_measure_vae.py:46-49): |z| > 2.15 is an outlier, ~3 % of N(0,1)
+    # samples; ~94 % of the pairs stay on one MUFU
+    for m in ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 2), 1.0, 10.0):
+        assert 1.03 < m < 1.10, m
+    # the triangle variant needs one attribute order per dim: there the whole dim falls back
+    assert set(ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 2), 1.0, 10.0, algo=3)) == {2.0}
+
+
+@pytest.mark.parametrize("algo", [2, 3])
+@pytest.mark.parametrize("case", ["delta10", "all_outliers", "nan_latent", "boundary_in_tile"])
+def test_outlier_segment_against_f64_oracle(ab, oracle_mod, algo, case):
+    B = 8192 + 300
+    g = torch.Generator().manual_seed(21)
+    z = torch.randn(B, 2, generator=g)
+    labels = torch.stack([torch.randn(B, generator=g), torch.randint(0, 7, (B,), generator=g).float()], dim=1)
+    delta = 10.0
+    if case == "all_outliers":
+        z = z * 0.01 + 5.0            # every |u| > 62: no inlier at all (and a shift the loss is invariant to)
+    elif case == "nan_latent":
+        delta = 1.0
+        z[17, 0] = float("inf")       # inf - inf = NaN in the reference too
+    elif case == "boundary_in_tile":
+        delta = 1.0
+        z[:100, 1] = 25.0             # exactly 100 outliers: the segment boundary falls inside a tile
+    ref_loss, ref_grad = oracle_mod.compute_reg_loss_multi(z.numpy(), labels.numpy(), (0, 1), 1.0, delta, f64=True)
+    zc = z.cuda().requires_grad_(True)
+    loss = ab.reg_loss_fused(zc, labels.cuda(), (0, 1), 1.0, delta, algo=algo)
+    loss.backward()
+    assert_loss_close(loss.item(), ref_loss)
+    if case == "nan_latent":
+        assert np.isnan(ref_loss) and torch.isnan(zc.grad[:, 0]).any()
+        assert_grad_close(zc.grad[:, 1].cpu().numpy(), ref_grad[:, 1])
+    else:
+        assert_grad_close(zc.grad.cpu().numpy(), ref_grad)
 
 
 # ------------------------------------------------------------------------------------------------
