@@ -63,6 +63,8 @@ SIGNATURES = {
                                                      ctypes.POINTER(_i64), _f, _f, _vp, _vp, _vp]),
     "arvae_shard_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_uint64), _vp]),
     "arvae_shard_destroy": (ctypes.c_int, [_vp]),
+    "arvae_timeline_enable": (None, [ctypes.c_int]),
+    "arvae_timeline_report": (ctypes.c_int, [ctypes.c_char_p, _i32]),
     "arvae_launch_count": (_i64, [ctypes.c_int]),
     "arvae_profile_enable": (None, [ctypes.c_int]),
     "arvae_profile_pair_kernel_ms": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),

@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(CSRC, "libarvae_b200.so")
+LIB = os.environ.get("ARVAE_LIB_OUT") or os.path.join(CSRC, "libarvae_b200.so")  # override: A/B experiments
 SOURCES = ["api.cu", "reg_dense.cu", "reg_sorted.cu", "sort.cu", "latent_head.cu", "music_attrs.cu", "eval_metrics.cu"]
 HEADERS = ["common.cuh", "reg_internal.cuh", os.path.join("..", "..", "include", "arvae_b200.h")]
 
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.environ.get("ARVAE_OBJ_DIR") or os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None)  # the image's CC points at a wrapper that breaks nvcc's host compile

@@ -58,6 +58,25 @@ void profile_end(cudaStream_t st) {
     P.n++;
 }
 
+// ---- optional step timeline: an event after each group of launches ----------------------------------
+constexpr int kTimelineMax = 256;
+struct Timeline {
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[kTimelineMax] = {};
+    const char *name[kTimelineMax] = {};
+};
+static thread_local Timeline g_tl;
+
+void timeline_mark(cudaStream_t st, const char *name) {
+    Timeline &T = g_tl;
+    if (!T.on || T.n >= kTimelineMax) return;
+    if (!T.ev[T.n]) cudaEventCreate(&T.ev[T.n]);
+    cudaEventRecord(T.ev[T.n], st);
+    T.name[T.n] = name;
+    T.n++;
+}
+
 int sm_count() {
     // immutable per-device cache (benign race: every thread computes the same value)
     static int cache[64] = {0};
@@ -137,6 +156,34 @@ int arvae_profile_pair_kernel_ms(float *sum_ms_out, int *n_out) {
     if (sum_ms_out) *sum_ms_out = sum;
     if (n_out) *n_out = n;
     P.n = 0;
+    return 0;
+}
+
+void arvae_timeline_enable(int on) {
+    g_tl.on = on != 0;
+    g_tl.n = 0;
+}
+
+// "name:ms;name:ms;..." -- milliseconds between consecutive marks recorded since arvae_timeline_enable(1); a mark named
+// "begin..." starts a new interval (its own delta is not reported).  Synchronises the recorded events; clears them.
+int arvae_timeline_report(char *buf, int32_t buf_bytes) {
+    Timeline &T = g_tl;
+    if (!buf || buf_bytes < 2) {
+        set_error("bad argument to timeline_report");
+        return ARVAE_E_BADARG;
+    }
+    int off = 0;
+    buf[0] = 0;
+    for (int i = 1; i < T.n; ++i) {
+        if (strncmp(T.name[i], "begin", 5) == 0) continue;
+        float ms = 0.f;
+        ARVAE_CUDA_TRY(cudaEventSynchronize(T.ev[i]));
+        ARVAE_CUDA_TRY(cudaEventElapsedTime(&ms, T.ev[i - 1], T.ev[i]));
+        const int w = snprintf(buf + off, (size_t)(buf_bytes - off), "%s:%.4f;", T.name[i], ms);
+        if (w < 0 || w >= buf_bytes - off) break;
+        off += w;
+    }
+    T.n = 0;
     return 0;
 }
 
@@ -230,12 +277,12 @@ int arvae_reg_loss_path_flags(int64_t B_total, int64_t n_rows, int32_t R, int32_
     }
     const SortedLayout LS = sorted_layout(B_total, n_rows, R, sm_count(), algo == ARVAE_ALGO_TRIANGLE);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int32_t tmp[3 * ARVAE_MAX_REG_DIMS + 1];
+    int32_t tmp[3 * ARVAE_MAX_REG_DIMS + 3];
     ARVAE_CUDA_TRY(cudaMemcpyAsync(tmp, reinterpret_cast<const char *>(workspace_dev) + LS.off_flags,
                                    sizeof(tmp), cudaMemcpyDeviceToHost, st));
     ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
     // whole-dim two-MUFU flag (triangle mode): report "no inliers"; else the inlier count of the segmented order
-    for (int r = 0; r < R; ++r) flags_out_host[r] = tmp[r] ? 0 : tmp[2 * ARVAE_MAX_REG_DIMS + 1 + r];
+    for (int r = 0; r < R; ++r) flags_out_host[r] = tmp[r] ? 0 : tmp[2 * ARVAE_MAX_REG_DIMS + 3 + r];
     return 0;
 }
 
@@ -483,6 +530,7 @@ int arvae_shard_create(int32_t rank, int32_t world, int64_t n_cap, int32_t R_cap
     }
     if (e == cudaSuccess) e = cudaMemset(C->comm, 0, C->comm_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&C->ws, C->ws_bytes);
+    if (e == cudaSuccess) e = cudaMemset(C->ws, 0, C->ws_bytes);  // the per-step flags start cleared; finalize re-clears them
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         cudaFree(C->comm);
@@ -637,6 +685,15 @@ int arvae_shard_reg_loss_host_f32(void *ctx, const float *z_local_host, int64_t 
     ARVAE_CUDA_TRY(cudaMemcpyAsync(&loss, C->h_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
     *loss_out_host = (float)loss;
+    return 0;
+}
+
+// experiments only (not in the public header): per-CTA globaltimer stamps of the last pair-kernel launch of this rank
+extern "C" __attribute__((visibility("default"))) int arvae_shard_debug_times(void *ctx, int64_t B_total, int32_t R,
+                                                                            unsigned long long *out_host, int32_t n_cta) {
+    ShardCtx *C = as_ctx(ctx);
+    const SortedLayout L = sorted_layout(B_total, B_total, R, sm_count(), false);
+    ARVAE_CUDA_TRY(cudaMemcpy(out_host, C->ws + L.off_dbg, sizeof(unsigned long long) * 2 * (size_t)n_cta, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -16,6 +16,8 @@ void count_launch(int n = 1);
 // pair-kernel timing hooks (no-ops unless arvae_profile_enable(1))
 void profile_begin(cudaStream_t st);
 void profile_end(cudaStream_t st);
+// named CUDA-event marks between the launches of a step (no-ops unless arvae_timeline_enable(1)); experiments only
+void timeline_mark(cudaStream_t st, const char *name);
 
 #define ARVAE_CUDA_TRY(expr)                                        \
     do {                                                            \

@@ -53,6 +53,17 @@ int run_pack_slice(const float *z, int64_t zrs, int64_t zcs, const float *lab, i
 int run_extract_perm(const unsigned long long *keys, int64_t B, int32_t *perm, cudaStream_t st);
 int run_sign_matrix(const float *a, int64_t stride, int64_t B, int8_t *out, cudaStream_t st);
 
+// Layout of the small int array `flags` of a sorted-path call: [0, 32) whole-dim two-MUFU flags (unsegmented keys),
+// [32] plan error, [33] some element of some dim needs the two-MUFU form, [34] "last CTA" ticket of the plan kernel,
+// [35, 67) per-dim non-finite latent bits (1: +-inf present, 2: NaN present), [67, 99) n_in per dim.
+constexpr int kFlagError = ARVAE_MAX_REG_DIMS;
+constexpr int kFlagAnyTwoMufu = ARVAE_MAX_REG_DIMS + 1;
+constexpr int kFlagTicket = ARVAE_MAX_REG_DIMS + 2;
+constexpr int kFlagNonFinite = ARVAE_MAX_REG_DIMS + 3;
+constexpr int kFlagNIn = 2 * ARVAE_MAX_REG_DIMS + 3;
+constexpr int kFlagInts = 3 * ARVAE_MAX_REG_DIMS + 3;
+constexpr int kFlagClearInts = kFlagNIn;  // n_in is always written, the rest is cleared per call
+
 // How sort.cu builds its 64-bit keys (see make_sort_key).
 struct KeySpec {
     const float *lab;
@@ -69,8 +80,33 @@ constexpr unsigned long long kKeyIdxMask = 0x7FFFFFFFull;  // segmented keys: lo
 __host__ __device__ static inline bool key_is_outlier(unsigned long long k) { return (k >> 63) != 0; }
 __host__ __device__ static inline unsigned int key_sortable_attr(unsigned long long k) { return (unsigned int)(k >> 31); }
 
-// ---- row-block sharding over NVLink peer memory (reg_shard.cuh) -------------------------------------------
+// ---- sorted runs (sort.cu: chunk_sort_kernel; reg_shard.cuh: runs_merge_kernel) ----------------------------
+// The batch is argsorted as T runs of <= kRunCap consecutive samples, each radix-sorted by one CTA, and the runs are
+// merged by rank (binary searches) into the global order.  On several GPUs the runs of a rank are its own samples,
+// stored straight into every peer's run slots over NVLink.  An element is one 16-byte store: it carries the step's
+// epoch, so a reader can tell on its own whether the element has arrived -- no fences or flags on the publish side.
+constexpr int kRunCap = 8192;
+constexpr int kMaxRuns = 64;
 constexpr int kMaxShardRanks = 16;
+struct __align__(16) RunElem {
+    unsigned long long key;  // [outlier:1][sortable attribute:32][global index:31]
+    float xs;                // sgn(f) * latent
+    unsigned int epoch;      // low 32 bits of the step's epoch (0 never occurs: buffers start zeroed)
+};
+// A run region holds, per (run, dim), kRunCap element slots followed by kRunPivots pivot slots: pivot j is a copy of
+// element kPivotStep * j, so that a reader can bound any key's rank in the run to one bucket with a single small load.
+constexpr int kPivotStep = 64;
+constexpr int kRunPivots = kRunCap / kPivotStep;
+constexpr int kRunSlotElems = kRunCap + kRunPivots;
+struct RunDest {             // where chunk_sort_kernel stores its sorted run: slot (run, dim) of every destination buffer
+    int n_dest, R_cap;
+    char *base[kMaxShardRanks];  // first byte of each destination's run region
+};
+__host__ __device__ static inline RunElem *run_slot(char *runs_base, int R_cap, int run, int r) {
+    return reinterpret_cast<RunElem *>(runs_base) + ((int64_t)run * R_cap + r) * kRunSlotElems;
+}
+
+// ---- row-block sharding over NVLink peer memory (reg_shard.cuh) -------------------------------------------
 
 // First bytes of every rank's communication buffer.
 struct ShardHeader {
@@ -85,10 +121,10 @@ struct ShardHeader {
 struct ShardView {
     int G, g;                   // ranks, this rank; G == 0: not a sharded step
     int R_cap, Gc;              // dims the run slots are sized for; pair-kernel CTAs per rank
-    int64_t n_cap;              // rows a run slot holds
+    int64_t n_cap;              // most rows a rank may hold
     int64_t row_off[kMaxShardRanks + 1];  // global index of every rank's first row in this step; [G] = B
     char *peer[kMaxShardRanks];
-    size_t off_flagA, off_flagB, off_keys, off_xs, off_acc;
+    size_t off_flagB, off_runs, off_acc;
 };
 
 // attribute-sorted path (sort.cu, reg_sorted.cu)
@@ -98,14 +134,20 @@ struct SortedLayout {
     int n_row_tiles, S;
     int64_t n_rr, F;
     int G_max;
+    int n_runs;     // sorted runs of <= kRunCap samples when the whole batch is sorted as runs (0: bitonic network instead)
     size_t acc_bytes;
-    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_cls8, off_cost8, off_combo, off_prefix, off_acc_g, off_acc_l,
+    size_t off_keys, off_Us, off_As, off_Es, off_perm, off_rowpos, off_flags, off_blockcnt, off_cls8, off_cost8, off_combo, off_prefix, off_runs, off_acc_g, off_acc_l,
         off_acc_s, off_lossp, off_dbg, off_colpart, off_eloss, bytes;
 };
 int64_t sort_padded_size(int64_t B);
 int run_sort_keys(const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, int64_t B,
                   int64_t N, unsigned long long *keys, cudaStream_t st);
 int run_sort_keys_spec(const KeySpec &spec, int R, int64_t B, int64_t N, unsigned long long *keys, cudaStream_t st);
+// Radix-sorts the n samples of `spec` as ceil(n / kRunCap) runs (global run indices first_run ...) and stores each run
+// into slot (run, dim) of every destination.  epoch_ctr: device counter of completed steps (elements carry *epoch_ctr
+// + 1), or null (elements carry 1: single GPU, stream order is enough).
+int run_chunk_sort(const KeySpec &spec, int R, int64_t n, int first_run, const RunDest &dest,
+                   const unsigned long long *epoch_ctr, cudaStream_t st);
 SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count, bool with_triangle = false);
 int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStream_t st);
 constexpr int64_t kSortedMinBatch = 8192;  // ARVAE_ALGO_AUTO switches to the sorted path from here
@@ -118,7 +160,8 @@ struct ShardCtx {
     size_t comm_bytes = 0;
     char *peer[kMaxShardRanks] = {};
     bool opened[kMaxShardRanks] = {};   // mapped with cudaIpcOpenMemHandle (to be closed)
-    size_t off_flagA = 0, off_flagB = 0, off_keys = 0, off_xs = 0, off_acc = 0;
+    size_t off_flagB = 0, off_runs = 0, off_acc = 0;
+    int runs_cap = 0;           // run slots per buffer
     char *ws = nullptr;         // private workspace (sorted columns, plan, ...)
     size_t ws_bytes = 0, off_mypos = 0;
     float *h_z = nullptr, *h_lab = nullptr, *h_gz = nullptr, *h_gc = nullptr;  // device staging of the host-buffer entry

@@ -1,5 +1,6 @@
-// reg_shard.cuh -- the attribute-regularization step sharded over the GPUs of one NVSwitch box, with the exchange
-// done by the kernels themselves over NVLink peer memory (included by reg_sorted.cu).
+// reg_shard.cuh -- sorted runs -> global sorted columns (single GPU and sharded), and the attribute-regularization
+// step sharded over the GPUs of one NVSwitch box with the exchange done by the kernels themselves over NVLink peer
+// memory (included by reg_sorted.cu).
 //
 // One process per GPU; rank g holds the samples its own encoder produced (z_local [n_g, Z], labels_local [n_g, A]).
 // The pair matrix is cut by ROW BLOCKS OF THE SORTED ORDER: every rank runs the same plan as a single GPU would
@@ -7,30 +8,33 @@
 // Gc.  Because row sums are fixed-point integers and the tile geometry is the single-GPU one, the loss and every
 // gradient element are BITWISE identical to the single-GPU result for any G.
 //
-//   (A) publish   each rank argsorts ITS OWN n_g rows per dim (sort.cu; 1/G of the sort work) and stores the sorted run
-//                 -- 64-bit key + latent, 12 bytes per element -- straight into the run slot g of EVERY peer's
-//                 communication buffer (NVLink stores), then raises flag A at every peer.          [all-gather]
-//   (B) merge     waits for the G flags, places every element of every run at its global sorted position by G - 1
-//                 binary searches in the other runs (keys are unique: attribute, then global index), which rebuilds
-//                 the single-GPU sorted columns on every rank; plan; pair kernel on this rank's CTA range, row sums
-//                 into this rank's accumulators (integer atomics); the last CTA publishes the rank's exact loss
-//                 partial and raises flag B at every peer.
+//   (A) publish   each rank radix-sorts ITS OWN rows per dim as runs of <= 8192 samples (sort.cu: one CTA per run,
+//                 1/G of the sort work) and stores every sorted element -- key, latent and the step's epoch in one
+//                 16-byte store -- straight into the run slots of EVERY peer's communication buffer (NVLink stores).
+//                 No fence, no flag: an element says itself whether it has arrived.                  [all-gather]
+//   (B) merge     every rank places every element of every run at its global sorted position (binary searches in
+//                 windows of the other runs staged in shared memory; keys are unique: attribute, then global
+//                 index), which rebuilds the single-GPU sorted columns on every rank; plan; pair kernel on this
+//                 rank's CTA range, row sums into this rank's accumulators (integer atomics); the last CTA
+//                 publishes the rank's exact loss partial and raises flag B at every peer.
 //   (C) finalize  waits for the G flags B, PULLS the row sums of its own samples from the accumulators of the 1-2
 //                 ranks that swept those sorted positions (NVLink loads), and all G loss partials -> grad_cols, loss.
 //                                                                                [gradient return + all-reduce]
-// No NCCL call and no host synchronisation in the step; flags are epoch counters, waits are bounded (a peer that
-// never signals turns the loss into NaN instead of hanging the GPU).
+// No NCCL call and no host synchronisation in the step; waits are bounded (a peer that never shows up turns the
+// loss into NaN instead of hanging the GPU).  System-scope fences cost ~7 us each on this platform and are avoided:
+// published elements validate themselves, and what peers pull lives in the producer's own L2, where a device-scope
+// fence before the flag store is enough.
 #pragma once
 
 namespace {
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ long long ld_relaxed_sys_s64(const long long *p) {
     long long v;
@@ -46,14 +50,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __device__ __forceinline__ ShardHeader *shard_header(const ShardView &v, int h) {
     return reinterpret_cast<ShardHeader *>(v.peer[h]);
 }
-__device__ __forceinline__ unsigned long long *shard_flags(const ShardView &v, int h, bool second) {
-    return reinterpret_cast<unsigned long long *>(v.peer[h] + (second ? v.off_flagB : v.off_flagA));
-}
-__device__ __forceinline__ unsigned long long *shard_run_keys(const ShardView &v, int h, int src, int r) {
-    return reinterpret_cast<unsigned long long *>(v.peer[h] + v.off_keys) + ((int64_t)src * v.R_cap + r) * v.n_cap;
-}
-__device__ __forceinline__ float *shard_run_xs(const ShardView &v, int h, int src, int r) {
-    return reinterpret_cast<float *>(v.peer[h] + v.off_xs) + ((int64_t)src * v.R_cap + r) * v.n_cap;
+__device__ __forceinline__ unsigned long long *shard_flags(const ShardView &v, int h) {
+    return reinterpret_cast<unsigned long long *>(v.peer[h] + v.off_flagB);
 }
 __device__ __forceinline__ acc_t *shard_acc(const ShardView &v, int h) {
     return reinterpret_cast<acc_t *>(v.peer[h] + v.off_acc);
@@ -61,128 +59,275 @@ __device__ __forceinline__ acc_t *shard_acc(const ShardView &v, int h) {
 
 constexpr unsigned long long kShardWaitNs = 4000000000ull;  // 4 s: far beyond any healthy step
 
-// Threads 0..G-1 of the CTA each wait for one peer's flag to reach `epoch`; everybody leaves together.
-__device__ __forceinline__ void shard_wait(const ShardView &v, bool second, unsigned long long epoch) {
+// Threads 0..G-1 of the CTA each wait for one peer's flag B to reach `epoch`; everybody leaves together.
+__device__ __forceinline__ void shard_wait(const ShardView &v, unsigned long long epoch) {
     if ((int)threadIdx.x < v.G) {
-        const unsigned long long *f = shard_flags(v, v.g, second) + threadIdx.x;
-        const unsigned long long t0 = global_timer_ns();
+        const unsigned long long *f = shard_flags(v, v.g) + threadIdx.x;
         volatile int *status = &shard_header(v, v.g)->status;
-        while (ld_acquire_sys_u64(f) < epoch) {
+        unsigned long long t0 = 0;
+        while (ld_volatile_u64(f) < epoch) {
             if (*status != 0) break;  // an earlier wait already gave up: do not stall again
-            if (global_timer_ns() - t0 > kShardWaitNs) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kShardWaitNs) {
                 atomicExch(&shard_header(v, v.g)->status, 1);
                 break;
             }
-            __nanosleep(64);
         }
     }
     __syncthreads();
 }
 
-// Tail of a kernel whose every CTA has finished writing data the peers will read: the last CTA to arrive raises this
-// rank's flag at every peer.  Callers have executed __threadfence_system() after their writes.
-__device__ __forceinline__ bool shard_last_cta(unsigned int *ticket, unsigned int n_cta) {
+// "Last CTA" ticket with device-scope fences: true in the CTA that arrives last, after which it sees what every
+// other CTA wrote before arriving.  The caller resets the ticket.
+__device__ __forceinline__ bool last_cta(unsigned int *ticket, unsigned int n_cta) {
     __shared__ int s_last;
+    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        s_last = atomicAdd(ticket, 1u) == n_cta - 1;
-    }
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == n_cta - 1;
     __syncthreads();
-    if (s_last) __threadfence_system();
+    if (s_last) __threadfence();
     return s_last != 0;
-}
-__device__ __forceinline__ void shard_signal(const ShardView &v, bool second, unsigned long long epoch) {
-    if ((int)threadIdx.x < v.G) st_release_sys_u64(shard_flags(v, (int)threadIdx.x, second) + v.g, epoch);
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
-// (A) publish this rank's sorted runs to every peer
+// merge T sorted runs into the global sorted columns
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-shard_publish_kernel(ShardView v, const unsigned long long *__restrict__ keys, int64_t N, const float *__restrict__ z,
-                     int64_t zrs, int64_t zcs, RegDims dims, float fsign) {
-    const int r = blockIdx.y;
-    const int64_t n = v.row_off[v.g + 1] - v.row_off[v.g];
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long epoch = shard_header(v, v.g)->epoch + 1;
-    if (p < n) {
-        const unsigned long long key = keys[(int64_t)r * N + p];
-        const int64_t i = (int64_t)(key & kKeyIdxMask) - v.row_off[v.g];
-        const float xs = signed_latent(__ldg(z + i * zrs + (int64_t)dims.zcol[r] * zcs), fsign);
-        for (int h = 0; h < v.G; ++h) {
-            shard_run_keys(v, h, v.g, r)[p] = key;
-            shard_run_xs(v, h, v.g, r)[p] = xs;
-        }
-    }
-    __threadfence_system();
-    if (shard_last_cta(&shard_header(v, v.g)->done_pub, gridDim.x * gridDim.y)) {
-        if (threadIdx.x == 0) shard_header(v, v.g)->done_pub = 0;
-        shard_signal(v, false, epoch);
-    }
-}
+struct RunSet {
+    int T, R_cap;                         // runs; dims the slots are sized for
+    int64_t run_off[kMaxRuns + 1];        // global index of each run's first sample; [T] = B
+    int blk_off[kMaxRuns + 1];            // prefix of ceil(n_t / 256): merge CTA -> run
+    char *base;                           // this GPU's run-slot region
+    const unsigned long long *epoch_ctr;  // non-null: elements are valid once they carry (uint32)(*epoch_ctr + 1)
+    int *status;                          // where a timed-out wait is recorded (with epoch_ctr)
+};
 
-// ------------------------------------------------------------------------------------------------------------
-// (B) merge the G runs into the global sorted columns
-// ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sortable_to_float_bits(unsigned int u) {  // inverse of sort.cu's float_to_sortable
     return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
 }
-__device__ __forceinline__ int64_t count_below(const unsigned long long *__restrict__ run, int64_t n, unsigned long long key) {
-    int64_t lo = 0, hi = n;  // first position whose key is >= `key`
+
+// One element of a run.  With validation the load bypasses L1 and spins until the element carries the step's epoch
+// (its 16 bytes were stored at once by the producer, possibly another GPU).
+template <bool VALIDATE>
+__device__ __forceinline__ uint4 load_run_elem(const RunElem *p, unsigned int epoch, int *status) {
+    if (!VALIDATE) return *reinterpret_cast<const uint4 *>(p);
+    uint4 v;
+    unsigned long long t0 = 0;
+    while (true) {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+        if (v.w == epoch) break;
+        if (*reinterpret_cast<volatile int *>(status) != 0) break;
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kShardWaitNs) {
+            atomicExch(status, 1);
+            break;
+        }
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned long long elem_key(const uint4 &e) { return ((unsigned long long)e.y << 32) | e.x; }
+
+template <bool VALIDATE>
+__device__ __forceinline__ int count_below_run(const RunElem *run, int n, unsigned long long key, unsigned int epoch, int *status) {
+    int lo = 0, hi = n;  // first position whose key is >= `key`
     while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (run[mid] < key) lo = mid + 1; else hi = mid;
+        const int mid = (lo + hi) >> 1;
+        if (elem_key(load_run_elem<VALIDATE>(run + mid, epoch, status)) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int count_below_smem(const unsigned long long *win, int n, unsigned long long key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (win[mid] < key) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-__global__ void __launch_bounds__(256)
-shard_merge_kernel(ShardView v, int64_t Bpad, float cabs, float *__restrict__ Xs, float *__restrict__ As,
-                   float *__restrict__ Es, int *__restrict__ perm, int *__restrict__ flags, int *__restrict__ mypos) {
-    const int r = blockIdx.y;
-    const int64_t B = v.row_off[v.G];
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    shard_wait(v, false, shard_header(v, v.g)->epoch + 1);
-    if (t >= Bpad) return;
+constexpr int kMergeThreads = 256;
+
+// One CTA per 256 consecutive elements of one run (and dim).  Their keys ascend, so inside any other run only the
+// window between the positions of the CTA's first and last key can interleave with them: two binary searches per
+// other run bound the windows, the windows are staged in shared memory, and every element finds its rank in each
+// window there.  Global position = own index in its run + the ranks in all other runs.
+template <bool VALIDATE>
+__global__ void __launch_bounds__(kMergeThreads)
+runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, float *__restrict__ As,
+                  float *__restrict__ Es, int *__restrict__ perm, int *__restrict__ flags, int *__restrict__ mypos,
+                  int64_t my_lo, int64_t my_hi, int64_t mypos_stride, int win_cap, int dbg) {
+    long long tk[6];
+    tk[0] = clock64();
+    extern __shared__ __align__(16) unsigned long long dyn_smem[];  // [T][kRunPivots] pivot keys, then [win_cap] window keys
+    unsigned long long *piv = dyn_smem;
+    unsigned long long *win = dyn_smem + (size_t)rs.T * kRunPivots;
+    __shared__ int s_lb[kMaxRuns], s_len[kMaxRuns], s_woff[kMaxRuns + 1];
+    __shared__ unsigned long long s_edge[2];
+    __shared__ int s_total;
+    const int r = blockIdx.y, tid = threadIdx.x;
+    const int64_t B = rs.run_off[rs.T];
     const int64_t base = (int64_t)r * Bpad;
-    if (t >= B) {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
-        Xs[base + t] = ARVAE_PAD_U;
-        As[base + t] = ARVAE_PAD_A;
-        Es[base + t] = 8.5070592e37f;
-        perm[base + t] = -1;
+    const int n_blocks = rs.blk_off[rs.T];
+    if ((int)blockIdx.x >= n_blocks) {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
+        const int64_t t = B + (int64_t)(blockIdx.x - n_blocks) * kMergeThreads + tid;
+        if (t < Bpad) {
+            Xs[base + t] = ARVAE_PAD_U;
+            As[base + t] = ARVAE_PAD_A;
+            Es[base + t] = 8.5070592e37f;
+            perm[base + t] = -1;
+        }
         return;
     }
-    int h = 0;
-    while (t >= v.row_off[h + 1]) ++h;  // input slot t = element p of run h
-    const int64_t p = t - v.row_off[h];
-    const unsigned long long key = shard_run_keys(v, v.g, h, r)[p];
-    int64_t pos = p;
-    for (int o = 0; o < v.G; ++o)
-        if (o != h) pos += count_below(shard_run_keys(v, v.g, o, r), v.row_off[o + 1] - v.row_off[o], key);
-    const float xs = shard_run_xs(v, v.g, h, r)[p];
-    const int64_t idx = (int64_t)(key & kKeyIdxMask);
-    Xs[base + pos] = xs;
-    As[base + pos] = sortable_to_float_bits(key_sortable_attr(key));  // NaNs come back as one quiet NaN: only compared
-    Es[base + pos] = key_is_outlier(key) ? 1.0f : exp2f(cabs * xs);
-    perm[base + pos] = (int)idx;
-    note_nonfinite(xs, flags, r);
-    if (h == v.g) mypos[(int64_t)r * v.n_cap + (idx - v.row_off[v.g])] = (int)pos;
-    if (t == 0) {  // inliers of the dim = keys below the outlier bit, over all runs
-        int64_t c = 0;
-        for (int o = 0; o < v.G; ++o)
-            c += count_below(shard_run_keys(v, v.g, o, r), v.row_off[o + 1] - v.row_off[o], 1ull << 63);
-        flags[kFlagNIn + r] = (int)c;
+    const unsigned int epoch = VALIDATE ? (unsigned int)(*rs.epoch_ctr + 1ull) : 1u;
+    int t = 0;
+    while ((int)blockIdx.x >= rs.blk_off[t + 1]) ++t;
+    const int n_t = (int)(rs.run_off[t + 1] - rs.run_off[t]);
+    const int p0 = ((int)blockIdx.x - rs.blk_off[t]) * kMergeThreads;
+    const int cnt = min(kMergeThreads, n_t - p0);
+    const RunElem *mine_run = run_slot(rs.base, rs.R_cap, t, r);
+    uint4 e = make_uint4(0, 0, 0, 0);
+    if (tid < cnt) e = load_run_elem<VALIDATE>(mine_run + p0 + tid, epoch, rs.status);
+    // pivots (every kPivotStep-th key) of all runs: one round of parallel loads
+    for (int i = tid; i < rs.T * kRunPivots; i += kMergeThreads) {
+        const int o = i / kRunPivots, j = i % kRunPivots;
+        const int n_o = (int)(rs.run_off[o + 1] - rs.run_off[o]);
+        piv[i] = (o != t && j * kPivotStep < n_o)
+                     ? elem_key(load_run_elem<VALIDATE>(run_slot(rs.base, rs.R_cap, o, r) + kRunCap + j, epoch, rs.status)) : ~0ull;
+    }
+    const unsigned long long key = elem_key(e);
+    if (tid == 0) s_edge[0] = key;
+    if (tid == cnt - 1) s_edge[1] = key;
+    __syncthreads();
+    tk[1] = clock64();
+    // Window of every other run that can interleave with this CTA's keys, to pivot granularity: with j pivots below a
+    // key K, K's rank in the run lies in [kPivotStep (j - 1), kPivotStep j].
+    if (tid < 2 * rs.T) {
+        const int o = tid >> 1, which = tid & 1;
+        const int n_o = (int)(rs.run_off[o + 1] - rs.run_off[o]);
+        const int np = (n_o + kPivotStep - 1) / kPivotStep;
+        const int j = o == t ? 0 : count_below_smem(piv + o * kRunPivots, np, s_edge[which]);
+        if (which == 0) s_lb[o] = j >= 1 ? kPivotStep * (j - 1) : 0;
+        else s_len[o] = min(kPivotStep * j, n_o);  // exclusive end, turned into a length below
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int o = 0; o < rs.T; ++o) {
+            s_len[o] = o == t ? 0 : s_len[o] - s_lb[o];
+            s_woff[o] = tot;
+            tot += s_len[o];
+        }
+        s_woff[rs.T] = tot;
+        s_total = tot;
+    }
+    __syncthreads();
+    const bool staged = s_total <= win_cap;
+    tk[2] = clock64();
+    if (staged) {
+        for (int o = 0; o < rs.T; ++o) {
+            const RunElem *ro = run_slot(rs.base, rs.R_cap, o, r) + s_lb[o];
+            for (int i = tid; i < s_len[o]; i += kMergeThreads)
+                win[s_woff[o] + i] = elem_key(load_run_elem<VALIDATE>(ro + i, epoch, rs.status));
+        }
+    }
+    __syncthreads();
+    tk[3] = clock64();
+    if (tid < cnt) {
+        int64_t pos = p0 + tid;
+        for (int o = 0; o < rs.T; ++o) {
+            if (o == t) continue;
+            pos += s_lb[o];
+            if (staged) pos += count_below_smem(win + s_woff[o], s_len[o], key);
+            else pos += count_below_run<VALIDATE>(run_slot(rs.base, rs.R_cap, o, r) + s_lb[o], s_len[o], key, epoch, rs.status);
+        }
+        const float xs = __uint_as_float(e.z);
+        const int64_t idx = (int64_t)(key & kKeyIdxMask);
+        Xs[base + pos] = xs;
+        As[base + pos] = sortable_to_float_bits(key_sortable_attr(key));  // NaNs come back as one quiet NaN: only compared
+        Es[base + pos] = key_is_outlier(key) ? 1.0f : exp2f(cabs * xs);
+        perm[base + pos] = (int)idx;
+        note_nonfinite(xs, flags, r);
+        if (key_is_outlier(key)) atomicOr(flags + kFlagAnyTwoMufu, 1);
+        if (mypos && idx >= my_lo && idx < my_hi) mypos[(int64_t)r * mypos_stride + (idx - my_lo)] = (int)pos;
+    }
+    if (dbg && blockIdx.x == 1 && blockIdx.y == 0 && tid == 0)
+        printf("runs_merge T=%d total window %d staged %d cycles: load %lld bounds %lld stage %lld rank+write %lld\n", rs.T, s_total,
+               (int)staged, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], (long long)clock64() - tk[3]);
+    if (blockIdx.x == 0) {  // inliers of the dim = keys below the outlier bit, over all runs
+        __shared__ int s_nin[kMaxRuns];
+        if (tid < rs.T)
+            s_nin[tid] = count_below_run<VALIDATE>(run_slot(rs.base, rs.R_cap, tid, r), (int)(rs.run_off[tid + 1] - rs.run_off[tid]),
+                                                   1ull << 63, epoch, rs.status);
+        __syncthreads();
+        if (tid == 0) {
+            int c = 0;
+            for (int o = 0; o < rs.T; ++o) c += s_nin[o];
+            flags[kFlagNIn + r] = c;
+        }
     }
 }
 
-// Last CTA of the pair kernel: this rank's exact loss partial -> its header, then flag B at every peer.
+// Fills `rs` for runs made of `n_parts` consecutive parts (ranks) of the batch, each cut into runs of kRunCap.
+static int fill_run_set(RunSet &rs, const int64_t *part_sizes, int n_parts, int *first_run_of_part /* [n_parts] or null */) {
+    rs.T = 0;
+    rs.run_off[0] = 0;
+    rs.blk_off[0] = 0;
+    for (int h = 0; h < n_parts; ++h) {
+        if (first_run_of_part) first_run_of_part[h] = rs.T;
+        for (int64_t done = 0; done < part_sizes[h]; done += kRunCap) {
+            if (rs.T >= kMaxRuns) return -1;
+            const int64_t n = part_sizes[h] - done < kRunCap ? part_sizes[h] - done : kRunCap;
+            rs.run_off[rs.T + 1] = rs.run_off[rs.T] + n;
+            rs.blk_off[rs.T + 1] = rs.blk_off[rs.T] + (int)ceil_div(n, kMergeThreads);
+            rs.T++;
+        }
+    }
+    return 0;
+}
+
+static int launch_runs_merge(const RunSet &rs, int R, int64_t Bpad, float cabs, float *Xs, float *As, float *Es, int *perm,
+                             int *flags, int *mypos, int64_t my_lo, int64_t my_hi, int64_t mypos_stride, cudaStream_t st) {
+    const int64_t B = rs.run_off[rs.T];
+    // expected window total ~ 256 (T - 1): stage up to 2x that (>= 4096 keys), within the opt-in shared memory
+    int win_cap = 2 * kMergeThreads * (rs.T > 1 ? rs.T - 1 : 1);
+    if (win_cap < 4096) win_cap = 4096;
+    if (win_cap > 24576) win_cap = 24576;
+    win_cap += 2 * kPivotStep * rs.T;  // pivot-granular windows are up to two buckets wider per run
+    constexpr size_t kMergeSmemMax = 200 * 1024;
+    const size_t piv_bytes = sizeof(unsigned long long) * (size_t)rs.T * kRunPivots;
+    if (piv_bytes + sizeof(unsigned long long) * (size_t)win_cap > kMergeSmemMax)
+        win_cap = (int)((kMergeSmemMax - piv_bytes) / sizeof(unsigned long long));
+    const size_t smem = piv_bytes + sizeof(unsigned long long) * (size_t)win_cap;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !attr_set[dev]) {
+        const int max_smem = 200 * 1024;
+        ARVAE_CUDA_TRY(cudaFuncSetAttribute(runs_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        ARVAE_CUDA_TRY(cudaFuncSetAttribute(runs_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set[dev] = true;
+    }
+    dim3 grid((unsigned)(rs.blk_off[rs.T] + ceil_div(Bpad - B, kMergeThreads)), (unsigned)R);
+    static const int dbg = getenv("ARVAE_DEBUG_PHASES") ? 1 : 0;
+    if (rs.epoch_ctr)
+        runs_merge_kernel<true><<<grid, kMergeThreads, smem, st>>>(rs, Bpad, cabs, Xs, As, Es, perm, flags, mypos, my_lo, my_hi,
+                                                                mypos_stride, win_cap, dbg);
+    else
+        runs_merge_kernel<false><<<grid, kMergeThreads, smem, st>>>(rs, Bpad, cabs, Xs, As, Es, perm, flags, mypos, my_lo, my_hi,
+                                                                 mypos_stride, win_cap, dbg);
+    ARVAE_LAUNCH_CHECK("runs_merge_kernel");
+    return 0;
+}
+
+// Last CTA of the pair kernel: this rank's exact loss partial -> its header, then flag B at every peer.  What the
+// peers pull afterwards (row accumulators, loss partial) lives in THIS GPU's L2; device-scope fences order it before
+// the flag stores.
 __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh /* shared memory, 2 * kDuoThreads, free by now */) {
     ShardHeader *hdr = shard_header(a.shard, a.shard.g);
     const unsigned long long epoch = hdr->epoch + 1;
-    if (!shard_last_cta(&hdr->done_pair, gridDim.x)) return;
+    if (!last_cta(&hdr->done_pair, gridDim.x)) return;
     acc_t th = 0, tl = 0;
     for (unsigned int u = threadIdx.x; u < gridDim.x; u += blockDim.x) {
         th += __ldcg(a.lossp + 2 * u);
@@ -202,10 +347,10 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh /* shared m
         hdr->loss_part[0] = sh[0];
         hdr->loss_part[1] = sh[kDuoThreads];
         hdr->done_pair = 0;
-        __threadfence_system();
+        __threadfence();
     }
     __syncthreads();
-    shard_signal(a.shard, true, epoch);
+    if ((int)threadIdx.x < a.shard.G) st_volatile_u64(shard_flags(a.shard, (int)threadIdx.x) + a.shard.g, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -214,14 +359,16 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh /* shared m
 __global__ void __launch_bounds__(256)
 shard_finalize_kernel(TilesArgs a, const int *__restrict__ mypos, int R, double gscale, double lscale,
                       double pad_per_row, float *__restrict__ grad_cols, double *__restrict__ loss_out,
-                      float *__restrict__ loss_f32_out) {
+                      float *__restrict__ loss_f32_out, int *__restrict__ flags_rw) {
     const ShardView &v = a.shard;
     ShardHeader *hdr = shard_header(v, v.g);
     const unsigned long long epoch = hdr->epoch + 1;
-    shard_wait(v, true, epoch);
+    shard_wait(v, epoch);
     const int64_t n = v.row_off[v.g + 1] - v.row_off[v.g];
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n * R, dim fastest (coalesced stores)
-    if (grad_cols && idx < n * R) {
+    const bool broken = *reinterpret_cast<volatile int *>(&hdr->status) != 0;  // a wait gave up: positions may be garbage
+    if (grad_cols && idx < n * R && broken) grad_cols[idx] = __int_as_float(0x7fc00000);
+    if (grad_cols && idx < n * R && !broken) {
         const int r = (int)(idx % R);
         const int64_t i = idx / R;
         const int64_t pos = mypos[(int64_t)r * v.n_cap + i];
@@ -251,12 +398,13 @@ shard_finalize_kernel(TilesArgs a, const int *__restrict__ mypos, int R, double 
             if (loss_f32_out) *loss_f32_out = (float)(total * lscale);
         }
     }
-    // the step is complete on this rank once every CTA is past its wait and its pulls: advance the epoch
-    if (shard_last_cta(&hdr->done_fin, gridDim.x)) {
+    // the step is complete on this rank once every CTA is past its wait and its pulls: clear the per-step flags for
+    // the next step's merge and advance the epoch
+    if (last_cta(&hdr->done_fin, gridDim.x)) {
+        if ((int)threadIdx.x < kFlagClearInts) flags_rw[threadIdx.x] = 0;
         if (threadIdx.x == 0) {
             hdr->done_fin = 0;
             hdr->epoch = epoch;
-            __threadfence();
         }
     }
 }
@@ -264,6 +412,11 @@ shard_finalize_kernel(TilesArgs a, const int *__restrict__ mypos, int R, double 
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+static int shard_runs_cap(int64_t n_cap, int G) {
+    const int64_t t = (int64_t)G * ceil_div(n_cap, kRunCap);
+    return (int)(t < kMaxRuns ? t : kMaxRuns);
+}
+
 size_t shard_comm_bytes(int64_t n_cap, int R_cap, int G, ShardCtx *fill) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -272,14 +425,13 @@ size_t shard_comm_bytes(int64_t n_cap, int R_cap, int G, ShardCtx *fill) {
         return o;
     };
     take(sizeof(ShardHeader));
-    const size_t fa = take(sizeof(unsigned long long) * kMaxShardRanks);
     const size_t fb = take(sizeof(unsigned long long) * kMaxShardRanks);
-    const size_t ok = take(sizeof(unsigned long long) * (size_t)G * R_cap * n_cap);
-    const size_t ox = take(sizeof(float) * (size_t)G * R_cap * n_cap);
+    const int runs_cap = shard_runs_cap(n_cap, G);
+    const size_t orn = take(sizeof(RunElem) * (size_t)runs_cap * R_cap * kRunSlotElems);
     const int64_t tiles = ceil_div((int64_t)G * n_cap, kTileRows);
     const size_t oa = take(sizeof(acc_t) * (size_t)R_cap * tiles * kTileRows);
     if (fill) {
-        fill->off_flagA = fa; fill->off_flagB = fb; fill->off_keys = ok; fill->off_xs = ox; fill->off_acc = oa;
+        fill->off_flagB = fb; fill->off_runs = orn; fill->off_acc = oa; fill->runs_cap = runs_cap;
     }
     return off;
 }
@@ -307,12 +459,23 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
         v.row_off[h + 1] = v.row_off[h] + S.n_all[h];
         v.peer[h] = C.peer[h];
     }
-    v.off_flagA = C.off_flagA; v.off_flagB = C.off_flagB; v.off_keys = C.off_keys; v.off_xs = C.off_xs; v.off_acc = C.off_acc;
+    v.off_flagB = C.off_flagB; v.off_runs = C.off_runs; v.off_acc = C.off_acc;
     const int64_t B = v.row_off[G], n_local = S.n_all[g];
     if (S.R < 1 || S.R > C.R_cap || B < 1 || B > (int64_t)kKeyIdxMask) {
         set_error("shard step: R=%d (capacity %d), B=%lld out of range", S.R, C.R_cap, (long long)B);
         return ARVAE_E_BADARG;
     }
+    RunSet rs;
+    memset(&rs, 0, sizeof(rs));
+    int first_run[kMaxShardRanks];
+    if (fill_run_set(rs, S.n_all, G, first_run) != 0 || rs.T > C.runs_cap) {
+        set_error("shard step: more than %d sorted runs", C.runs_cap);
+        return ARVAE_E_BADARG;
+    }
+    rs.R_cap = C.R_cap;
+    rs.base = C.comm + C.off_runs;
+    rs.epoch_ctr = &reinterpret_cast<ShardHeader *>(C.comm)->epoch;
+    rs.status = &reinterpret_cast<ShardHeader *>(C.comm)->status;
     const int phases = S.phases ? S.phases : 7;
     const SortedLayout L = sorted_layout(B, B, S.R, sm_count(), false);
     if (L.bytes > C.off_mypos) {
@@ -320,9 +483,7 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
         return ARVAE_E_WORKSPACE;
     }
     char *ws = C.ws;
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + L.off_keys);
-    int *flags = reinterpret_cast<int *>(ws + L.off_flags);
-    int *n_in = flags + kFlagNIn;
+    int *flags = reinterpret_cast<int *>(ws + L.off_flags);  // cleared at creation and by every finalize
     int *perm = reinterpret_cast<int *>(ws + L.off_perm);
     int *mypos = reinterpret_cast<int *>(ws + C.off_mypos);
     const double c = 2.0 * (double)S.factor * 1.4426950408889634074;
@@ -342,7 +503,7 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
     a.Es = reinterpret_cast<float *>(ws + L.off_Es);
     a.cabs = cabs;
     a.flags = flags;
-    a.n_in = n_in;
+    a.n_in = flags + kFlagNIn;
     a.Bpad = L.Bpad; a.n_rows = B;
     a.n_row_tiles = L.n_row_tiles; a.S = L.S; a.F = L.F; a.n_rr = L.n_rr;
     a.P = golden_stride(L.S);
@@ -354,51 +515,56 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
     a.acc_g = reinterpret_cast<acc_t *>(C.comm + C.off_acc);
     a.lossp = reinterpret_cast<acc_t *>(ws + L.off_lossp);
     a.B = B;
+    a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
     a.shard = v;
     const bool want_grad = S.grad_cols_out != nullptr;
 
     if (phases & 1) {
-        const int64_t N = sort_padded_size(n_local > 0 ? n_local : 1);
         KeySpec spec;
         spec.lab = S.lab; spec.lrs = S.lrs; spec.lcs = S.lcs;
         spec.z = S.z; spec.zrs = S.zrs; spec.zcs = S.zcs;
         spec.fsign = fsign; spec.cabs = cabs; spec.segment = 1;
         spec.idx_offset = v.row_off[g];
         spec.dims = S.dims;
-        int rc = run_sort_keys_spec(spec, S.R, n_local, N, keys, st);
+        RunDest dest;
+        memset(&dest, 0, sizeof(dest));
+        dest.n_dest = G; dest.R_cap = C.R_cap;
+        for (int h = 0; h < G; ++h) dest.base[h] = C.peer[h] + C.off_runs;
+        timeline_mark(st, "begin");
+        int rc = run_chunk_sort(spec, S.R, n_local, first_run[g], dest, rs.epoch_ctr, st);
         if (rc) return rc;
-        dim3 gp((unsigned)ceil_div(n_local > 0 ? n_local : 1, 256), (unsigned)S.R);
-        shard_publish_kernel<<<gp, 256, 0, st>>>(v, keys, N, S.z, S.zrs, S.zcs, S.dims, fsign);
-        ARVAE_LAUNCH_CHECK("shard_publish_kernel");
+        timeline_mark(st, "sort+publish");
     }
     if (phases & 2) {
-        ARVAE_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * kFlagClearInts, st));
-        dim3 gm((unsigned)ceil_div(L.Bpad, 256), (unsigned)S.R);
-        shard_merge_kernel<<<gm, 256, 0, st>>>(v, L.Bpad, cabs, const_cast<float *>(a.Xs), const_cast<float *>(a.As),
-                                               const_cast<float *>(a.Es), perm, flags, mypos);
-        ARVAE_LAUNCH_CHECK("shard_merge_kernel");
-        // Only now may the accumulators be cleared: every peer has published this step's run, hence finished pulling
-        // the previous step's row sums from them.
-        if (want_grad) ARVAE_CUDA_TRY(cudaMemsetAsync(a.acc_g, 0, L.acc_bytes, st));
+        timeline_mark(st, "begin B");
+        int rc = launch_runs_merge(rs, S.R, L.Bpad, cabs, const_cast<float *>(a.Xs), const_cast<float *>(a.As),
+                                   const_cast<float *>(a.Es), perm, flags, mypos, v.row_off[g], v.row_off[g + 1], C.n_cap, st);
+        if (rc) return rc;
+        timeline_mark(st, "wait+merge");
+        // The plan kernel also clears the row accumulators.  That is safe only now: every peer has published this
+        // step's runs (the merge saw them), hence finished pulling the previous step's row sums.
         int *combo_cost = reinterpret_cast<int *>(ws + L.off_combo);
-        plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);
+        plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost, want_grad ? 1 : 0,
+                                                             reinterpret_cast<unsigned int *>(flags + kFlagTicket));
         ARVAE_LAUNCH_CHECK("plan_classes_kernel");
-        plan_scan_kernel<<<1, 1024, 0, st>>>(combo_cost, L.n_rr, a.prefix);
-        ARVAE_LAUNCH_CHECK("plan_scan_kernel");
+        timeline_mark(st, "plan");
         profile_begin(st);
         launch_tiles(a, (int)Gc, want_grad, false, st);
         profile_end(st);
         ARVAE_LAUNCH_CHECK("reg_tiles_kernel");
+        timeline_mark(st, "pairs");
     }
     if (phases & 4) {
+        timeline_mark(st, "begin C");
         RegProblem P;
         P.B = B; P.gamma = S.gamma; P.factor = S.factor;
         double lscale, gscale, pad_per_row;
         reg_scales(P, L.Bpad, lscale, gscale, pad_per_row);
         const int64_t work = n_local * S.R;
         shard_finalize_kernel<<<(unsigned)(work > 0 ? ceil_div(work, 256) : 1), 256, 0, st>>>(
-            a, mypos, S.R, gscale, lscale, pad_per_row, S.grad_cols_out, S.loss_out, S.loss_f32_out);
+            a, mypos, S.R, gscale, lscale, pad_per_row, S.grad_cols_out, S.loss_out, S.loss_f32_out, flags);
         ARVAE_LAUNCH_CHECK("shard_finalize_kernel");
+        timeline_mark(st, "wait+finalize");
     }
     return 0;
 }

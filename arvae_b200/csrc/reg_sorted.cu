@@ -44,14 +44,6 @@ constexpr int kStageCols = 2048;                   // columns staged per __synct
 static_assert(kTileRows / (kTileThreads / 32) == kTileRI * 32, "a warp owns kTileRI x 32 consecutive rows");
 static_assert(kTileThreads / 32 <= 16, "class word holds 16 warps");
 
-// Layout of the small int array `flags` of a call: [0, 32) whole-dim two-MUFU flags (unsegmented keys), [32] plan
-// error, [33, 65) per-dim non-finite latent bits (1: +-inf present, 2: NaN present), [65, 97) n_in per dim.
-constexpr int kFlagError = ARVAE_MAX_REG_DIMS;
-constexpr int kFlagNonFinite = ARVAE_MAX_REG_DIMS + 1;
-constexpr int kFlagNIn = 2 * ARVAE_MAX_REG_DIMS + 1;
-constexpr int kFlagInts = 3 * ARVAE_MAX_REG_DIMS + 1;
-constexpr int kFlagClearInts = kFlagNIn;  // n_in is always written, the rest is cleared per call
-
 // The fixed-point row sums cannot carry NaN, so non-finite latents are flagged when the columns are built and
 // the outputs are patched to what the reference's float arithmetic gives: the loss is NaN, a row with a non-finite
 // latent has a NaN gradient (inf - inf on its diagonal), and a NaN latent poisons every row of its dim.
@@ -114,6 +106,7 @@ sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
         perm[o] = (int)idx;
         // unsegmented keys (triangle mode): one out-of-range element sends the whole dim to the two-MUFU form
         if (unsegmented && !(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + r, 1);
+        if (!(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + kFlagAnyTwoMufu, 1);
         note_nonfinite(xs, flags, r);
         note_segment_boundary(kr, k, B, flags + kFlagNIn + r);
     } else {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
@@ -202,8 +195,9 @@ __device__ __forceinline__ float rcp_newton(float x) {
 }
 
 #ifndef ARVAE_NR_PAIRS
-#define ARVAE_NR_PAIRS 0  // of every 16 pairs of the 1-MUFU constant-sign loop, how many use rcp_newton (measured: 3 -> +2..4 %; off by
-                          // default so that the kernel stays a plain 1-MUFU-per-pair loop whose roofline is the XU pipe)
+#define ARVAE_NR_PAIRS 3  // of every 16 pairs of the 1-MUFU constant-sign loop, how many use rcp_newton.  Measured on the C4
+                          // workload (pair kernel, ms): 0 -> 5.86, 2 -> 5.67, 3 -> 5.60, 4 -> 5.81, 5 -> 6.14, 6 -> 6.36: with 3
+                          // of 16 reciprocals on the FMA pipe the XU pipe (13/16 MUFU per pair) and the issue slots balance.
 #endif
 
 template <bool MUFU1>
@@ -369,6 +363,8 @@ struct TilesArgs {
     int c_first;                // first of those CTAs this launch runs (0 on a single GPU)
     int64_t n_rr;               // R * n_row_tiles
     int force_general;          // treat every tile as general (unsorted input / debugging)
+    int dual;                   // the launch is a pair of kernels: the one-MUFU-only build runs when no element of any
+                                // dim needs the two-MUFU form (flags[kFlagAnyTwoMufu] == 0), the complete one otherwise
     // plan (plan_classes_kernel / plan_scan_kernel): per fine unit in VISITING order u = rr * S + s'
     unsigned int *cls8;         // [F] per warp w: 2-bit tile class (bits 2w..2w+1) and tanh form (bit 16+w: 1 = two MUFU)
     unsigned short *cost8;      // [F] modelled cost of the unit (sum over the tile's warps)
@@ -409,8 +405,13 @@ __device__ __forceinline__ int class_cost(int cls, bool mufu1) {
 // (|u| <= 62): the warp's rows must all lie before n_in[r] and so must the sub-chunk's real columns.  A warp's row
 // group or a sub-chunk that straddles the inlier / outlier boundary is not attribute-sorted across it, so its end
 // points say nothing about its range: such tiles run the general loop.
+// The kernel also clears the row accumulators of its row tile (clear_acc bits: 1 gradient, 2 loss, 4 signs), and the
+// CTA that finishes last turns the per-row-tile totals into the cost prefix the pair kernel cuts its ranges from
+// (one launch instead of memset + plan + scan).
+__device__ void plan_scan_tail(const int *__restrict__ combo_cost, int64_t n_rr, long long *__restrict__ prefix);
+
 __global__ void __launch_bounds__(256)
-plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost) {
+plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost, int clear_acc, unsigned int *__restrict__ ticket) {
     __shared__ float wmin[kTileThreads / 32], wmax[kTileThreads / 32];
     __shared__ int whas[kTileThreads / 32], win[kTileThreads / 32], wmixed[kTileThreads / 32];
     __shared__ int sred[8];
@@ -464,9 +465,53 @@ plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost) {
         for (int w = 0; w < 8; ++w) t += sred[w];
         combo_cost[rr] = t;
     }
+    for (int i = threadIdx.x; i < kTileRows; i += 256) {
+        if (clear_acc & 1) a.acc_g[rr * kTileRows + i] = 0;
+        if (clear_acc & 2) a.acc_l[rr * kTileRows + i] = 0;
+        if (clear_acc & 4) a.acc_s[rr * kTileRows + i] = 0;
+    }
+    // last CTA: exclusive prefix of the row-tile costs
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0;
+    plan_scan_tail(combo_cost, a.n_rr, a.prefix);
 }
 
-// prefix[rr] = sum of combo_cost[0..rr) ; prefix[n_rr] = T.   One CTA.
+// prefix[rr] = sum of combo_cost[0..rr) ; prefix[n_rr] = T, by one CTA of 256 threads (the last plan CTA).
+__device__ void plan_scan_tail(const int *__restrict__ combo_cost, int64_t n_rr, long long *__restrict__ prefix) {
+    __shared__ long long swarp[8];
+    __shared__ long long scarry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) scarry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_rr; base += 256) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = i < n_rr ? (long long)__ldcg(combo_cost + i) : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        long long before = scarry;
+        for (int w = 0; w < warp; ++w) before += swarp[w];
+        const long long excl = before + incl - v;
+        if (i < n_rr) prefix[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 255) scarry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n_rr] = scarry;
+}
+
+// prefix[rr] = sum of combo_cost[0..rr) ; prefix[n_rr] = T.   One CTA.  (triangle variant's plan)
 __global__ void __launch_bounds__(1024)
 plan_scan_kernel(const int *__restrict__ combo_cost, int64_t n_rr, long long *__restrict__ prefix) {
     __shared__ long long swarp[32];
@@ -601,7 +646,11 @@ __device__ __forceinline__ void half_barrier(int half) {
 
 __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh);  // reg_shard.cuh
 
-template <bool GRAD, bool SIGNS>
+// ONLY1: a build of the kernel without the two-MUFU loops (the common case: image configs at delta = 1 have no
+// outliers).  The complete kernel carries eight inlined pair loops; dropping four of them shortens the code the
+// instruction caches have to hold and was measured 2-4 % faster on the all-inlier workload, so the host launches both
+// builds and each decides on the device flag whether it is the one to run (the other exits at once).
+template <bool GRAD, bool SIGNS, bool ONLY1>
 __global__ void __launch_bounds__(kDuoThreads, 1)
 reg_tiles_kernel(TilesArgs a) {
     extern __shared__ __align__(16) float stage[];  // [2 halves][3 arrays][kStageCols] = kDuoStageBytes (dynamic)
@@ -611,6 +660,7 @@ reg_tiles_kernel(TilesArgs a) {
     __shared__ unsigned int s_claimed;   // units granted so far (may overshoot N)
     __shared__ int s_grant[2][2];        // per half: first unit (linear) and count of the current grant
 
+    if (a.dual && (a.flags[kFlagAnyTwoMufu] != 0) == ONLY1) return;  // the other build's turn
     const long long c = (long long)a.c_first + blockIdx.x;
     if (a.dbg_times && threadIdx.x == 0) {
         unsigned long long t;
@@ -731,7 +781,7 @@ reg_tiles_kernel(TilesArgs a) {
                 const int sub = w * kSubCols;
                 const unsigned int word = a.cls8[rr * a.S + sp + w];
                 const int cls = (word >> (2 * warp)) & 3;        // planned class of this warp's tile
-                const bool mufu1 = ((word >> (16 + warp)) & 1u) == 0u;  // planned tanh form
+                const bool mufu1 = ONLY1 || ((word >> (16 + warp)) & 1u) == 0u;  // planned tanh form
                 if (mufu1) sweep_subchunk<true, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
                 else sweep_subchunk<false, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
             }
@@ -838,10 +888,12 @@ static int tiles_ctas_per_sm() {
     int &v = cache[current_device_slot()];
     if (v == 0) {
         int n = 0;
-        cudaFuncSetAttribute(reg_tiles_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
-        cudaFuncSetAttribute(reg_tiles_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
-        cudaFuncSetAttribute(reg_tiles_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<true, false>, kDuoThreads, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaFuncSetAttribute(reg_tiles_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoStageBytes);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reg_tiles_kernel<true, false, false>, kDuoThreads, kDuoStageBytes);
         if (e != cudaSuccess || n <= 0) {
             (void)cudaGetLastError();
             n = 1;
@@ -851,10 +903,21 @@ static int tiles_ctas_per_sm() {
     return v;
 }
 
-static void launch_tiles(const TilesArgs &a, int n_cta, bool want_grad, bool want_signs, cudaStream_t st) {
-    if (want_signs) reg_tiles_kernel<true, true><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
-    else if (want_grad) reg_tiles_kernel<true, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
-    else reg_tiles_kernel<false, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+static void launch_tiles(TilesArgs a, int n_cta, bool want_grad, bool want_signs, cudaStream_t st) {
+    if (want_signs) {  // parity instrumentation: the complete build only
+        a.dual = 0;
+        reg_tiles_kernel<true, true, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+        return;
+    }
+    a.dual = 1;  // both builds; the device flag decides which one works
+    if (want_grad) {
+        reg_tiles_kernel<true, false, true><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+        reg_tiles_kernel<true, false, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+    } else {
+        reg_tiles_kernel<false, false, true><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+        reg_tiles_kernel<false, false, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+    }
+    count_launch();
 }
 
 void reg_scales(const RegProblem &P, int64_t Bpad, double &lscale, double &gscale, double &pad_per_row) {
@@ -897,6 +960,10 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
     L.off_cost8 = take(sizeof(unsigned short) * (size_t)L.F);
     L.off_combo = take(sizeof(int) * (size_t)L.n_rr);
     L.off_prefix = take(sizeof(long long) * (size_t)(L.n_rr + 1));
+    // run slots of the radix chunk sort + rank merge (all rows of one GPU); larger batches keep the bitonic network
+    L.n_runs = (n_rows == B_total && !with_triangle && ceil_div(B_total > 0 ? B_total : 1, kRunCap) <= kMaxRuns)
+                   ? (int)ceil_div(B_total > 0 ? B_total : 1, kRunCap) : 0;
+    L.off_runs = take(sizeof(RunElem) * (size_t)L.n_runs * R * kRunSlotElems);
     // row accumulators: gradient, loss, sign sums -- contiguous so that one memset clears the ones in use
     L.acc_bytes = sizeof(acc_t) * (size_t)L.n_rr * kTileRows;
     L.off_acc_g = take(L.acc_bytes);
@@ -909,6 +976,8 @@ SortedLayout sorted_layout(int64_t B_total, int64_t n_rows, int R, int sm_count,
     L.bytes = off;
     return L;
 }
+
+#include "reg_shard.cuh"
 
 int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStream_t st) {
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + L.off_keys);
@@ -943,17 +1012,43 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     spec.segment = triangle ? 0 : 1;
     spec.idx_offset = 0;
     spec.dims = P.dims;
-    int rc = run_sort_keys_spec(spec, P.R, P.B, L.N, keys, st);
-    if (rc) return rc;
+    timeline_mark(st, "begin");
     ARVAE_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int) * kFlagClearInts, st));
-    dim3 gg((unsigned)ceil_div(L.Bpad, 256), (unsigned)P.R);
-    sorted_gather_kernel<<<gg, 256, 0, st>>>(keys, L.N, P.z, P.zrs, P.zcs, P.lab, P.lrs, P.lcs, P.dims,
-                                             P.B, L.Bpad, fsign, cabs, Xs, As, Es, perm, flags,
-                                             P.row_begin, P.row_end, all_rows ? nullptr : blockcnt, triangle ? 1 : 0);
-    ARVAE_LAUNCH_CHECK("sorted_gather_kernel");
+    int rc = 0;
+    if (L.n_runs > 0 && all_rows && !triangle && n_rows > 0) {
+        // radix-sorted runs of <= kRunCap samples, merged by rank: the same pipeline a sharded step runs per GPU
+        RunSet rs;
+        memset(&rs, 0, sizeof(rs));
+        const int64_t sizes[1] = {P.B};
+        if (fill_run_set(rs, sizes, 1, nullptr) != 0) {
+            set_error("internal: run set overflow");
+            return ARVAE_E_BADARG;
+        }
+        rs.R_cap = P.R;
+        rs.base = ws + L.off_runs;
+        RunDest dest;
+        memset(&dest, 0, sizeof(dest));
+        dest.n_dest = 1; dest.R_cap = P.R; dest.base[0] = ws + L.off_runs;
+        rc = run_chunk_sort(spec, P.R, P.B, 0, dest, nullptr, st);
+        if (rc) return rc;
+        timeline_mark(st, "sort");
+        rc = launch_runs_merge(rs, P.R, L.Bpad, cabs, Xs, As, Es, perm, flags, nullptr, 0, 0, 0, st);
+        if (rc) return rc;
+        timeline_mark(st, "merge");
+    } else {
+        rc = run_sort_keys_spec(spec, P.R, P.B, L.N, keys, st);
+        if (rc) return rc;
+        timeline_mark(st, "sort");
+        dim3 gg((unsigned)ceil_div(L.Bpad, 256), (unsigned)P.R);
+        sorted_gather_kernel<<<gg, 256, 0, st>>>(keys, L.N, P.z, P.zrs, P.zcs, P.lab, P.lrs, P.lcs, P.dims,
+                                                 P.B, L.Bpad, fsign, cabs, Xs, As, Es, perm, flags,
+                                                 P.row_begin, P.row_end, all_rows ? nullptr : blockcnt, triangle ? 1 : 0);
+        ARVAE_LAUNCH_CHECK("sorted_gather_kernel");
+        timeline_mark(st, "gather");
+    }
     if (!all_rows && n_rows > 0) {
         dim3 gs((unsigned)ceil_div(L.Bpad, 1024), (unsigned)P.R);
-        row_select_kernel<<<gs, 1024, 0, st>>>(perm, blockcnt, (int)gg.x, P.B, L.Bpad, P.row_begin, P.row_end,
+        row_select_kernel<<<gs, 1024, 0, st>>>(perm, blockcnt, (int)ceil_div(L.Bpad, 256), P.B, L.Bpad, P.row_begin, P.row_end,
                                                n_rows, rowpos);
         ARVAE_LAUNCH_CHECK("row_select_kernel");
     }
@@ -987,21 +1082,15 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     if (triangle) return run_reg_tri_tail(P, L, a, perm, combo_cost, ws, st);
 
     if (n_rows > 0) {
-        // the accumulators in use are contiguous: gradient [, loss [, signs]]
-        if (want_grad || a.acc_l || a.acc_s) {
-            const size_t first = want_grad ? L.off_acc_g : (a.acc_l ? L.off_acc_l : L.off_acc_s);
-            const size_t last = a.acc_s ? L.off_acc_s + sizeof(int) * (size_t)L.n_rr * kTileRows
-                                        : (a.acc_l ? L.off_acc_l + L.acc_bytes : L.off_acc_g + L.acc_bytes);
-            ARVAE_CUDA_TRY(cudaMemsetAsync(ws + first, 0, last - first, st));
-        }
-        plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost);
+        plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost, (want_grad ? 1 : 0) | (a.acc_l ? 2 : 0) | (a.acc_s ? 4 : 0),
+                                                             reinterpret_cast<unsigned int *>(flags + kFlagTicket));
         ARVAE_LAUNCH_CHECK("plan_classes_kernel");
-        plan_scan_kernel<<<1, 1024, 0, st>>>(combo_cost, L.n_rr, a.prefix);
-        ARVAE_LAUNCH_CHECK("plan_scan_kernel");
+        timeline_mark(st, "plan");
         profile_begin(st);
         launch_tiles(a, a.G, want_grad, want_signs, st);
         profile_end(st);
         ARVAE_LAUNCH_CHECK("reg_tiles_kernel");
+        timeline_mark(st, "pairs");
     }
 
     double lscale, gscale, pad_per_row;
@@ -1011,9 +1100,8 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
         a, perm, P.R, P.row_begin, n_rows > 0 ? a.G : 0, gscale, lscale, pad_per_row, P.grad_cols_out, P.row_loss_out,
         P.row_sign_out, P.loss_out, P.loss_f32_out);
     ARVAE_LAUNCH_CHECK("reg_tiles_epilogue_kernel");
+    timeline_mark(st, "epilogue");
     return 0;
 }
-
-#include "reg_shard.cuh"
 
 }  // namespace arvae

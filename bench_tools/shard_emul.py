@@ -82,11 +82,54 @@ def main():
         torch.cuda.synchronize()
         if it >= 3:
             single.append(e0.elapsed_time(e1))
+    # warm timeline of rank 0 (events between its launches; no L2 flush inside the step)
+    import ctypes
+    buf = ctypes.create_string_buffer(4096)
+    tl = {}
+    for it in range(5):
+        for phase in (1, 2, 4):
+            for g, h in enumerate(grp.ranks):
+                if g == 0:
+                    lib.arvae_timeline_enable(1)
+                h.step(zp[g], lp[g], dims, dims, n_all, c["gamma"], c["delta"], True, phase)
+                if g == 0:
+                    lib.arvae_timeline_report(buf, 4096)
+                    lib.arvae_timeline_enable(0)
+                    for item in buf.value.decode().split(";"):
+                        if item:
+                            k, v = item.rsplit(":", 1)
+                            tl.setdefault(k, []).append(float(v))
+            torch.cuda.synchronize()
+    timeline = {k: round(statistics.median(v) * 1e3, 1) for k, v in tl.items()}
+    tl1 = {}
+    for it in range(5):
+        lib.arvae_timeline_enable(1)
+        arvae_b200.reg_loss_rows(z, lab, dims, c["gamma"], c["delta"], 0, B, algo=arvae_b200.ALGO_SORTED)
+        lib.arvae_timeline_report(buf, 4096)
+        lib.arvae_timeline_enable(0)
+        for item in buf.value.decode().split(";"):
+            if item:
+                k, v = item.rsplit(":", 1)
+                tl1.setdefault(k, []).append(float(v))
+    timeline1 = {k: round(statistics.median(v) * 1e3, 1) for k, v in tl1.items()}
+    cta = None
+    if os.environ.get("ARVAE_DEBUG_TIMES"):
+        import numpy as np
+        lib.arvae_shard_debug_times.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32]
+        arr = np.zeros((148, 2), dtype=np.uint64)
+        lib.arvae_shard_debug_times(grp.ranks[0].ctx, B, len(dims), arr.ctypes.data_as(ctypes.c_void_p), 148)
+        t = arr.astype(np.int64)
+        t = t[t[:, 1] > 0]
+        t0 = t[:, 0].min()
+        st, en = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3
+        cta = {"n": int(len(t)), "start_spread_us": float(st.max()), "end_min_p10_med_p90_max_us": [float(en.min()), float(np.percentile(en, 10)), float(np.median(en)), float(np.percentile(en, 90)), float(en.max())],
+               "mean_busy_us": float(np.mean(en - st))}
     med = {k: statistics.median(v) for k, v in times.items()}
     out = {"world": G, "B": B, "rank0_publish_ms": med[1], "rank0_merge_plan_pair_ms": med[2], "rank0_finalize_ms": med[4],
            "rank0_pair_kernel_ms": statistics.median(pair_ms) if pair_ms else None,
            "rank0_step_ms": med[1] + med[2] + med[4], "single_gpu_fwd_ms": statistics.median(single),
            "fixed_ms": med[1] + med[2] + med[4] - (statistics.median(pair_ms) if pair_ms else 0.0),
+           "rank0_timeline_us": timeline, "single_gpu_timeline_us": timeline1, "rank0_cta_times": cta,
            "note": "flushed L2 before every timed phase; events bracket the launches of rank 0 only (cold start of each phase)"}
     print(json.dumps(out))
     grp.close()

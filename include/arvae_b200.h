@@ -279,6 +279,14 @@ ARVAE_API int arvae_reg_sign_matrix_i8(const float *labels_dev, int64_t lab_stri
 ARVAE_API void arvae_profile_enable(int on);
 ARVAE_API int arvae_profile_pair_kernel_ms(float *sum_ms_out, int *n_out);
 
+/*
+ * Step timeline for experiments: while enabled, the library records a CUDA event after each group of launches of a step
+ * (sort, gather / merge, plan, pair kernel, epilogue ...) on the caller's stream.  arvae_timeline_report synchronises
+ * them and writes "name:milliseconds;..." (the time between consecutive marks) into buf, then clears the list.
+ */
+ARVAE_API void arvae_timeline_enable(int on);
+ARVAE_API int arvae_timeline_report(char *buf, int32_t buf_bytes);
+
 /* Number of kernel launches issued through the library (all threads) since the last reset. */
 ARVAE_API int64_t arvae_launch_count(int reset);
 
