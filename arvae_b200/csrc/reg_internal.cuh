@@ -160,7 +160,7 @@ struct ShardCtx {
     size_t comm_bytes = 0;
     char *peer[kMaxShardRanks] = {};
     bool opened[kMaxShardRanks] = {};   // mapped with cudaIpcOpenMemHandle (to be closed)
-    size_t off_flagB = 0, off_runs = 0, off_acc = 0;
+    size_t off_flagB = 0, off_runs = 0, off_pos = 0, off_acc = 0;
     int runs_cap = 0;           // run slots per buffer
     char *ws = nullptr;         // private workspace (sorted columns, plan, ...)
     size_t ws_bytes = 0, off_mypos = 0;
@@ -176,7 +176,7 @@ struct ShardStep {
     float gamma, factor;
     double *loss_out; float *loss_f32_out;  // [1] global loss (device)
     float *grad_cols_out;                   // [n_local, R] or null
-    int phases;                             // bit 0: sort + publish, bit 1: merge + plan + pair kernel, bit 2: finalize; 0 = all
+    int phases;                             // bit 0: sort + publish, bit 1: rank own runs, bit 2: apply + plan + pair kernel, bit 3: finalize; 0 = all
 };
 size_t shard_comm_bytes(int64_t n_cap, int R_cap, int G, ShardCtx *fill);
 size_t shard_ws_bytes(int64_t n_cap, int R_cap, int G, size_t *off_mypos);

@@ -95,6 +95,17 @@ __device__ __forceinline__ bool last_cta(unsigned int *ticket, unsigned int n_ct
 // ------------------------------------------------------------------------------------------------------------
 // merge T sorted runs into the global sorted columns
 // ------------------------------------------------------------------------------------------------------------
+// Where a sharded step's merge stores the global positions of a rank's own run elements: slot (run, dim) of every
+// rank's position region, element i of the run at [i] as {position, epoch} in one 8-byte store.  n_dest == 0: the
+// merge writes the sorted columns itself (single GPU: every run is its own).
+struct PosDest {
+    int n_dest;
+    char *base[kMaxShardRanks];
+};
+__host__ __device__ static inline uint2 *pos_slot(char *pos_base, int R_cap, int run, int r) {
+    return reinterpret_cast<uint2 *>(pos_base) + ((int64_t)run * R_cap + r) * kRunCap;
+}
+
 struct RunSet {
     int T, R_cap;                         // runs; dims the slots are sized for
     int64_t run_off[kMaxRuns + 1];        // global index of each run's first sample; [T] = B
@@ -111,13 +122,18 @@ __device__ __forceinline__ float sortable_to_float_bits(unsigned int u) {  // in
 // One element of a run.  With validation the load bypasses L1 and spins until the element carries the step's epoch
 // (its 16 bytes were stored at once by the producer, possibly another GPU).
 template <bool VALIDATE>
-__device__ __forceinline__ uint4 load_run_elem(const RunElem *p, unsigned int epoch, int *status) {
+__device__ __forceinline__ uint4 load_run_elem_once(const RunElem *p) {
     if (!VALIDATE) return *reinterpret_cast<const uint4 *>(p);
     uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+template <bool VALIDATE>
+__device__ __forceinline__ uint4 load_run_elem(const RunElem *p, unsigned int epoch, int *status) {
+    uint4 v = load_run_elem_once<VALIDATE>(p);
+    if (!VALIDATE) return v;
     unsigned long long t0 = 0;
-    while (true) {
-        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-        if (v.w == epoch) break;
+    while (v.w != epoch) {
         if (*reinterpret_cast<volatile int *>(status) != 0) break;
         const unsigned long long now = global_timer_ns();
         if (t0 == 0) t0 = now;
@@ -125,8 +141,25 @@ __device__ __forceinline__ uint4 load_run_elem(const RunElem *p, unsigned int ep
             atomicExch(status, 1);
             break;
         }
+        v = load_run_elem_once<VALIDATE>(p);
     }
     return v;
+}
+// Keys of up to NB elements (null pointer: skipped), all loads in flight together; only an element that has not
+// arrived yet is waited for.
+template <bool VALIDATE, int NB>
+__device__ __forceinline__ void load_run_keys(const RunElem *(&ptr)[NB], unsigned long long (&key)[NB], unsigned int epoch,
+                                              int *status) {
+    uint4 v[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+        if (ptr[k]) v[k] = load_run_elem_once<VALIDATE>(ptr[k]);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        if (!ptr[k]) continue;
+        if (VALIDATE && v[k].w != epoch) v[k] = load_run_elem<VALIDATE>(ptr[k], epoch, status);
+        key[k] = ((unsigned long long)v[k].y << 32) | v[k].x;
+    }
 }
 __device__ __forceinline__ unsigned long long elem_key(const uint4 &e) { return ((unsigned long long)e.y << 32) | e.x; }
 
@@ -150,17 +183,49 @@ __device__ __forceinline__ int count_below_smem(const unsigned long long *win, i
 
 constexpr int kMergeThreads = 256;
 
+// n_in[r] = inliers of the dim = keys below the outlier bit, over all runs (one CTA per dim calls this).
+template <bool VALIDATE>
+__device__ __forceinline__ void count_inliers(const RunSet &rs, int r, unsigned int epoch, int *__restrict__ flags) {
+    __shared__ int s_nin[kMaxRuns];
+    const int tid = threadIdx.x;
+    if (tid < rs.T)
+        s_nin[tid] = count_below_run<VALIDATE>(run_slot(rs.base, rs.R_cap, tid, r), (int)(rs.run_off[tid + 1] - rs.run_off[tid]),
+                                               1ull << 63, epoch, rs.status);
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0;
+        for (int o = 0; o < rs.T; ++o) c += s_nin[o];
+        flags[kFlagNIn + r] = c;
+    }
+}
+
+// Writes one run element into the sorted columns of dim r at its global position.
+__device__ __forceinline__ void place_run_elem(const uint4 &e, int64_t pos, int64_t base, float cabs, float *__restrict__ Xs,
+                                               float *__restrict__ As, float *__restrict__ Es, int *__restrict__ perm,
+                                               int *__restrict__ flags, int r) {
+    const unsigned long long key = elem_key(e);
+    const float xs = __uint_as_float(e.z);
+    Xs[base + pos] = xs;
+    As[base + pos] = sortable_to_float_bits(key_sortable_attr(key));  // NaNs come back as one quiet NaN: only compared
+    Es[base + pos] = key_is_outlier(key) ? 1.0f : exp2f(cabs * xs);
+    perm[base + pos] = (int)(key & kKeyIdxMask);
+    note_nonfinite(xs, flags, r);
+    if (key_is_outlier(key)) atomicOr(flags + kFlagAnyTwoMufu, 1);
+}
+
 // One CTA per 256 consecutive elements of one run (and dim).  Their keys ascend, so inside any other run only the
 // window between the positions of the CTA's first and last key can interleave with them: two binary searches per
 // other run bound the windows, the windows are staged in shared memory, and every element finds its rank in each
 // window there.  Global position = own index in its run + the ranks in all other runs.
+// On one GPU the CTA then writes its elements into the sorted columns.  In a sharded step every rank ranks only ITS
+// OWN runs (1/G of the searches, and of the L2 traffic of the windows) and stores the positions into every peer's
+// position slots; runs_apply_kernel then moves all elements of all runs to their positions on every rank.
 template <bool VALIDATE>
 __global__ void __launch_bounds__(kMergeThreads)
 runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, float *__restrict__ As,
                   float *__restrict__ Es, int *__restrict__ perm, int *__restrict__ flags, int *__restrict__ mypos,
-                  int64_t my_lo, int64_t my_hi, int64_t mypos_stride, int win_cap, int dbg) {
-    long long tk[6];
-    tk[0] = clock64();
+                  int64_t my_lo, int64_t my_hi, int64_t mypos_stride, int win_cap, PosDest pd, int blk_begin, int dbg) {
+    long long tk[6]; tk[0] = clock64();
     extern __shared__ __align__(16) unsigned long long dyn_smem[];  // [T][kRunPivots] pivot keys, then [win_cap] window keys
     unsigned long long *piv = dyn_smem;
     unsigned long long *win = dyn_smem + (size_t)rs.T * kRunPivots;
@@ -171,8 +236,9 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
     const int64_t B = rs.run_off[rs.T];
     const int64_t base = (int64_t)r * Bpad;
     const int n_blocks = rs.blk_off[rs.T];
-    if ((int)blockIdx.x >= n_blocks) {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
-        const int64_t t = B + (int64_t)(blockIdx.x - n_blocks) * kMergeThreads + tid;
+    const int blk = blk_begin + (int)blockIdx.x;
+    if (blk >= n_blocks) {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
+        const int64_t t = B + (int64_t)(blk - n_blocks) * kMergeThreads + tid;
         if (t < Bpad) {
             Xs[base + t] = ARVAE_PAD_U;
             As[base + t] = ARVAE_PAD_A;
@@ -183,20 +249,33 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
     }
     const unsigned int epoch = VALIDATE ? (unsigned int)(*rs.epoch_ctr + 1ull) : 1u;
     int t = 0;
-    while ((int)blockIdx.x >= rs.blk_off[t + 1]) ++t;
+    while (blk >= rs.blk_off[t + 1]) ++t;
     const int n_t = (int)(rs.run_off[t + 1] - rs.run_off[t]);
-    const int p0 = ((int)blockIdx.x - rs.blk_off[t]) * kMergeThreads;
+    const int p0 = (blk - rs.blk_off[t]) * kMergeThreads;
     const int cnt = min(kMergeThreads, n_t - p0);
     const RunElem *mine_run = run_slot(rs.base, rs.R_cap, t, r);
     uint4 e = make_uint4(0, 0, 0, 0);
-    if (tid < cnt) e = load_run_elem<VALIDATE>(mine_run + p0 + tid, epoch, rs.status);
-    // pivots (every kPivotStep-th key) of all runs: one round of parallel loads
-    for (int i = tid; i < rs.T * kRunPivots; i += kMergeThreads) {
-        const int o = i / kRunPivots, j = i % kRunPivots;
-        const int n_o = (int)(rs.run_off[o + 1] - rs.run_off[o]);
-        piv[i] = (o != t && j * kPivotStep < n_o)
-                     ? elem_key(load_run_elem<VALIDATE>(run_slot(rs.base, rs.R_cap, o, r) + kRunCap + j, epoch, rs.status)) : ~0ull;
+    if (tid < cnt) e = load_run_elem_once<VALIDATE>(mine_run + p0 + tid);
+    // pivots (every kPivotStep-th key) of all other runs: the loads of a thread are in flight together
+    constexpr int kBatch = 4;
+    for (int i0 = tid; i0 < rs.T * kRunPivots; i0 += kBatch * kMergeThreads) {
+        const RunElem *ptr[kBatch];
+        unsigned long long key[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int i = i0 + k * kMergeThreads;
+            const int o = i / kRunPivots, j = i % kRunPivots;
+            ptr[k] = nullptr;
+            key[k] = ~0ull;
+            if (i < rs.T * kRunPivots && o != t && j * kPivotStep < (int)(rs.run_off[o + 1] - rs.run_off[o]))
+                ptr[k] = run_slot(rs.base, rs.R_cap, o, r) + kRunCap + j;
+        }
+        load_run_keys<VALIDATE, kBatch>(ptr, key, epoch, rs.status);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+            if (i0 + k * kMergeThreads < rs.T * kRunPivots) piv[i0 + k * kMergeThreads] = key[k];
     }
+    if (VALIDATE && tid < cnt && e.w != epoch) e = load_run_elem<VALIDATE>(mine_run + p0 + tid, epoch, rs.status);
     const unsigned long long key = elem_key(e);
     if (tid == 0) s_edge[0] = key;
     if (tid == cnt - 1) s_edge[1] = key;
@@ -213,24 +292,46 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
         else s_len[o] = min(kPivotStep * j, n_o);  // exclusive end, turned into a length below
     }
     __syncthreads();
-    if (tid == 0) {
-        int tot = 0;
-        for (int o = 0; o < rs.T; ++o) {
-            s_len[o] = o == t ? 0 : s_len[o] - s_lb[o];
-            s_woff[o] = tot;
-            tot += s_len[o];
+    if (tid < 32) {  // lengths and their exclusive prefix (T <= 64: two entries per lane)
+        int l0 = 0, l1 = 0;
+        const int o0 = 2 * tid, o1 = 2 * tid + 1;
+        if (o0 < rs.T && o0 != t) l0 = s_len[o0] - s_lb[o0];
+        if (o1 < rs.T && o1 != t) l1 = s_len[o1] - s_lb[o1];
+        const int mine = l0 + l1;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += v;
         }
-        s_woff[rs.T] = tot;
-        s_total = tot;
+        const int excl = incl - mine;
+        if (o0 < rs.T) { s_len[o0] = l0; s_woff[o0] = excl; }
+        if (o1 < rs.T) { s_len[o1] = l1; s_woff[o1] = excl + l0; }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tid == 0) { s_woff[rs.T] = tot; s_total = tot; }
     }
     __syncthreads();
-    const bool staged = s_total <= win_cap;
+    const int total = s_total;
+    const bool staged = total <= win_cap;
     tk[2] = clock64();
     if (staged) {
-        for (int o = 0; o < rs.T; ++o) {
-            const RunElem *ro = run_slot(rs.base, rs.R_cap, o, r) + s_lb[o];
-            for (int i = tid; i < s_len[o]; i += kMergeThreads)
-                win[s_woff[o] + i] = elem_key(load_run_elem<VALIDATE>(ro + i, epoch, rs.status));
+        for (int i0 = tid; i0 < total; i0 += kBatch * kMergeThreads) {
+            const RunElem *ptr[kBatch];
+            unsigned long long wk[kBatch];
+            int o = 0;
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const int i = i0 + k * kMergeThreads;
+                ptr[k] = nullptr;
+                if (i < total) {
+                    while (i >= s_woff[o + 1]) ++o;  // runs with an empty window (the own run among them) are skipped
+                    ptr[k] = run_slot(rs.base, rs.R_cap, o, r) + s_lb[o] + (i - s_woff[o]);
+                }
+            }
+            load_run_keys<VALIDATE, kBatch>(ptr, wk, epoch, rs.status);
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k)
+                if (ptr[k]) win[i0 + k * kMergeThreads] = wk[k];
         }
     }
     __syncthreads();
@@ -243,31 +344,66 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
             if (staged) pos += count_below_smem(win + s_woff[o], s_len[o], key);
             else pos += count_below_run<VALIDATE>(run_slot(rs.base, rs.R_cap, o, r) + s_lb[o], s_len[o], key, epoch, rs.status);
         }
-        const float xs = __uint_as_float(e.z);
         const int64_t idx = (int64_t)(key & kKeyIdxMask);
-        Xs[base + pos] = xs;
-        As[base + pos] = sortable_to_float_bits(key_sortable_attr(key));  // NaNs come back as one quiet NaN: only compared
-        Es[base + pos] = key_is_outlier(key) ? 1.0f : exp2f(cabs * xs);
-        perm[base + pos] = (int)idx;
-        note_nonfinite(xs, flags, r);
-        if (key_is_outlier(key)) atomicOr(flags + kFlagAnyTwoMufu, 1);
+        if (pd.n_dest > 0) {
+            const uint2 pe = make_uint2((unsigned int)pos, epoch);
+            for (int h = 0; h < pd.n_dest; ++h) pos_slot(pd.base[h], rs.R_cap, t, r)[p0 + tid] = pe;
+        } else {
+            place_run_elem(e, pos, base, cabs, Xs, As, Es, perm, flags, r);
+        }
         if (mypos && idx >= my_lo && idx < my_hi) mypos[(int64_t)r * mypos_stride + (idx - my_lo)] = (int)pos;
     }
     if (dbg && blockIdx.x == 1 && blockIdx.y == 0 && tid == 0)
-        printf("runs_merge T=%d total window %d staged %d cycles: load %lld bounds %lld stage %lld rank+write %lld\n", rs.T, s_total,
-               (int)staged, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], (long long)clock64() - tk[3]);
-    if (blockIdx.x == 0) {  // inliers of the dim = keys below the outlier bit, over all runs
-        __shared__ int s_nin[kMaxRuns];
-        if (tid < rs.T)
-            s_nin[tid] = count_below_run<VALIDATE>(run_slot(rs.base, rs.R_cap, tid, r), (int)(rs.run_off[tid + 1] - rs.run_off[tid]),
-                                                   1ull << 63, epoch, rs.status);
-        __syncthreads();
-        if (tid == 0) {
-            int c = 0;
-            for (int o = 0; o < rs.T; ++o) c += s_nin[o];
-            flags[kFlagNIn + r] = c;
+        printf("runs_merge T=%d window %d staged %d cycles: load %lld bounds %lld stage %lld rank+write %lld\n", rs.T, total, (int)staged,
+               tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], (long long)clock64() - tk[3]);
+    if (blockIdx.x == 0 && pd.n_dest == 0) count_inliers<VALIDATE>(rs, r, epoch, flags);
+}
+
+// A sharded step's second half of the merge: every element of every run of dim r goes to the position its owner
+// computed (runs_merge_kernel, stored into this rank's position slots over NVLink).  Same grid as a full merge.
+__global__ void __launch_bounds__(kMergeThreads)
+runs_apply_kernel(RunSet rs, char *__restrict__ pos_base, int64_t Bpad, float cabs, float *__restrict__ Xs,
+                  float *__restrict__ As, float *__restrict__ Es, int *__restrict__ perm, int *__restrict__ flags) {
+    const int r = blockIdx.y, tid = threadIdx.x;
+    const int64_t B = rs.run_off[rs.T];
+    const int64_t base = (int64_t)r * Bpad;
+    const int n_blocks = rs.blk_off[rs.T];
+    if ((int)blockIdx.x >= n_blocks) {  // padding, as in the merge
+        const int64_t t = B + (int64_t)(blockIdx.x - n_blocks) * kMergeThreads + tid;
+        if (t < Bpad) {
+            Xs[base + t] = ARVAE_PAD_U;
+            As[base + t] = ARVAE_PAD_A;
+            Es[base + t] = 8.5070592e37f;
+            perm[base + t] = -1;
         }
+        return;
     }
+    const unsigned int epoch = (unsigned int)(*rs.epoch_ctr + 1ull);
+    int t = 0;
+    while ((int)blockIdx.x >= rs.blk_off[t + 1]) ++t;
+    const int n_t = (int)(rs.run_off[t + 1] - rs.run_off[t]);
+    const int i = ((int)blockIdx.x - rs.blk_off[t]) * kMergeThreads + tid;
+    if (i < n_t) {
+        const RunElem *ep = run_slot(rs.base, rs.R_cap, t, r) + i;
+        const uint2 *pp = pos_slot(pos_base, rs.R_cap, t, r) + i;
+        uint4 e = load_run_elem_once<true>(ep);  // both loads in flight together
+        uint2 pe;
+        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(pe.x), "=r"(pe.y) : "l"(pp) : "memory");
+        if (e.w != epoch) e = load_run_elem<true>(ep, epoch, rs.status);
+        unsigned long long t0 = 0;
+        while (pe.y != epoch) {
+            if (*reinterpret_cast<volatile int *>(rs.status) != 0) break;
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kShardWaitNs) {
+                atomicExch(rs.status, 1);
+                break;
+            }
+            asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(pe.x), "=r"(pe.y) : "l"(pp) : "memory");
+        }
+        if (pe.y == epoch && (int64_t)pe.x < B) place_run_elem(e, (int64_t)pe.x, base, cabs, Xs, As, Es, perm, flags, r);
+    }
+    if (blockIdx.x == 0) count_inliers<true>(rs, r, epoch, flags);
 }
 
 // Fills `rs` for runs made of `n_parts` consecutive parts (ranks) of the batch, each cut into runs of kRunCap.
@@ -288,8 +424,10 @@ static int fill_run_set(RunSet &rs, const int64_t *part_sizes, int n_parts, int 
     return 0;
 }
 
+// Merge CTAs [blk_begin, blk_begin + n_blk) of the run set (n_blk < 0: all of them plus the padding CTAs).
 static int launch_runs_merge(const RunSet &rs, int R, int64_t Bpad, float cabs, float *Xs, float *As, float *Es, int *perm,
-                             int *flags, int *mypos, int64_t my_lo, int64_t my_hi, int64_t mypos_stride, cudaStream_t st) {
+                             int *flags, int *mypos, int64_t my_lo, int64_t my_hi, int64_t mypos_stride, const PosDest &pd,
+                             int blk_begin, int n_blk, cudaStream_t st) {
     const int64_t B = rs.run_off[rs.T];
     // expected window total ~ 256 (T - 1): stage up to 2x that (>= 4096 keys), within the opt-in shared memory
     int win_cap = 2 * kMergeThreads * (rs.T > 1 ? rs.T - 1 : 1);
@@ -309,14 +447,16 @@ static int launch_runs_merge(const RunSet &rs, int R, int64_t Bpad, float cabs, 
         ARVAE_CUDA_TRY(cudaFuncSetAttribute(runs_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[dev] = true;
     }
-    dim3 grid((unsigned)(rs.blk_off[rs.T] + ceil_div(Bpad - B, kMergeThreads)), (unsigned)R);
+    if (n_blk < 0) n_blk = (int)(rs.blk_off[rs.T] + ceil_div(Bpad - B, kMergeThreads));
+    if (n_blk == 0) return 0;
+    dim3 grid((unsigned)n_blk, (unsigned)R);
     static const int dbg = getenv("ARVAE_DEBUG_PHASES") ? 1 : 0;
     if (rs.epoch_ctr)
         runs_merge_kernel<true><<<grid, kMergeThreads, smem, st>>>(rs, Bpad, cabs, Xs, As, Es, perm, flags, mypos, my_lo, my_hi,
-                                                                mypos_stride, win_cap, dbg);
+                                                                mypos_stride, win_cap, pd, blk_begin, dbg);
     else
         runs_merge_kernel<false><<<grid, kMergeThreads, smem, st>>>(rs, Bpad, cabs, Xs, As, Es, perm, flags, mypos, my_lo, my_hi,
-                                                                 mypos_stride, win_cap, dbg);
+                                                                 mypos_stride, win_cap, pd, blk_begin, dbg);
     ARVAE_LAUNCH_CHECK("runs_merge_kernel");
     return 0;
 }
@@ -347,10 +487,14 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh /* shared m
         hdr->loss_part[0] = sh[0];
         hdr->loss_part[1] = sh[kDuoThreads];
         hdr->done_pair = 0;
-        __threadfence();
     }
     __syncthreads();
-    if ((int)threadIdx.x < a.shard.G) st_volatile_u64(shard_flags(a.shard, (int)threadIdx.x) + a.shard.g, epoch);
+    // Every CTA's row-sum atomics were ordered before its ticket at device scope, and this CTA saw the last ticket: one
+    // system-scope fence in each signalling thread (fences are cumulative) orders all of it before the flag a peer sees.
+    if ((int)threadIdx.x < a.shard.G) {
+        __threadfence_system();
+        st_volatile_u64(shard_flags(a.shard, (int)threadIdx.x) + a.shard.g, epoch);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -428,10 +572,11 @@ size_t shard_comm_bytes(int64_t n_cap, int R_cap, int G, ShardCtx *fill) {
     const size_t fb = take(sizeof(unsigned long long) * kMaxShardRanks);
     const int runs_cap = shard_runs_cap(n_cap, G);
     const size_t orn = take(sizeof(RunElem) * (size_t)runs_cap * R_cap * kRunSlotElems);
+    const size_t opo = take(sizeof(uint2) * (size_t)runs_cap * R_cap * kRunCap);
     const int64_t tiles = ceil_div((int64_t)G * n_cap, kTileRows);
     const size_t oa = take(sizeof(acc_t) * (size_t)R_cap * tiles * kTileRows);
     if (fill) {
-        fill->off_flagB = fb; fill->off_runs = orn; fill->off_acc = oa; fill->runs_cap = runs_cap;
+        fill->off_flagB = fb; fill->off_runs = orn; fill->off_pos = opo; fill->off_acc = oa; fill->runs_cap = runs_cap;
     }
     return off;
 }
@@ -476,7 +621,7 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
     rs.base = C.comm + C.off_runs;
     rs.epoch_ctr = &reinterpret_cast<ShardHeader *>(C.comm)->epoch;
     rs.status = &reinterpret_cast<ShardHeader *>(C.comm)->status;
-    const int phases = S.phases ? S.phases : 7;
+    const int phases = S.phases ? S.phases : 15;
     const SortedLayout L = sorted_layout(B, B, S.R, sm_count(), false);
     if (L.bytes > C.off_mypos) {
         set_error("shard step: workspace too small");
@@ -537,10 +682,27 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
     }
     if (phases & 2) {
         timeline_mark(st, "begin B");
+        // this rank's runs only: positions of their elements -> every peer's position slots
+        PosDest pd;
+        memset(&pd, 0, sizeof(pd));
+        pd.n_dest = G;
+        for (int h = 0; h < G; ++h) pd.base[h] = C.peer[h] + C.off_pos;
+        const int run_end = g + 1 < G ? first_run[g + 1] : rs.T;
         int rc = launch_runs_merge(rs, S.R, L.Bpad, cabs, const_cast<float *>(a.Xs), const_cast<float *>(a.As),
-                                   const_cast<float *>(a.Es), perm, flags, mypos, v.row_off[g], v.row_off[g + 1], C.n_cap, st);
+                                   const_cast<float *>(a.Es), perm, flags, mypos, v.row_off[g], v.row_off[g + 1], C.n_cap, pd,
+                                   rs.blk_off[first_run[g]], rs.blk_off[run_end] - rs.blk_off[first_run[g]], st);
         if (rc) return rc;
-        timeline_mark(st, "wait+merge");
+        timeline_mark(st, "rank own runs");
+    }
+    if (phases & 4) {
+        timeline_mark(st, "begin C");
+        {   // every element of every run to its position (waits for the peers' elements and positions)
+            dim3 grid((unsigned)(rs.blk_off[rs.T] + ceil_div(L.Bpad - B, kMergeThreads)), (unsigned)S.R);
+            runs_apply_kernel<<<grid, kMergeThreads, 0, st>>>(rs, C.comm + C.off_pos, L.Bpad, cabs, const_cast<float *>(a.Xs),
+                                                             const_cast<float *>(a.As), const_cast<float *>(a.Es), perm, flags);
+            ARVAE_LAUNCH_CHECK("runs_apply_kernel");
+        }
+        timeline_mark(st, "wait+apply");
         // The plan kernel also clears the row accumulators.  That is safe only now: every peer has published this
         // step's runs (the merge saw them), hence finished pulling the previous step's row sums.
         int *combo_cost = reinterpret_cast<int *>(ws + L.off_combo);
@@ -554,8 +716,8 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
         ARVAE_LAUNCH_CHECK("reg_tiles_kernel");
         timeline_mark(st, "pairs");
     }
-    if (phases & 4) {
-        timeline_mark(st, "begin C");
+    if (phases & 8) {
+        timeline_mark(st, "begin D");
         RegProblem P;
         P.B = B; P.gamma = S.gamma; P.factor = S.factor;
         double lscale, gscale, pad_per_row;

@@ -649,7 +649,10 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh);  // reg_s
 // ONLY1: a build of the kernel without the two-MUFU loops (the common case: image configs at delta = 1 have no
 // outliers).  The complete kernel carries eight inlined pair loops; dropping four of them shortens the code the
 // instruction caches have to hold and was measured 2-4 % faster on the all-inlier workload, so the host launches both
-// builds and each decides on the device flag whether it is the one to run (the other exits at once).
+// builds and each decides on the device flag whether it is the one to run (the other exits at once).  (Both builds
+// as two instantiations of the body inside ONE kernel was measured too: 3.7 % slower than the pair of launches; ptxas's
+// schedule of the pair loops is sensitive even to the prologue -- a variant of find_unit that located both ends of the
+// range in one pass changed it and cost 2 %.)
 template <bool GRAD, bool SIGNS, bool ONLY1>
 __global__ void __launch_bounds__(kDuoThreads, 1)
 reg_tiles_kernel(TilesArgs a) {
@@ -792,7 +795,6 @@ reg_tiles_kernel(TilesArgs a) {
     lhi = warp_sum(lhi);
     llo = warp_sum(llo);
     if ((threadIdx.x & 31) == 0) { sred[0][threadIdx.x >> 5] = lhi; sred[1][threadIdx.x >> 5] = llo; }
-    if (a.shard.G > 0) __threadfence_system();  // this thread's row-accumulator atomics are visible to the peers before the signal
     __syncthreads();
     if (threadIdx.x == 0) {
         acc_t th = 0, tl = 0;
@@ -806,6 +808,7 @@ reg_tiles_kernel(TilesArgs a) {
             a.dbg_times[2 * blockIdx.x + 1] = tt;
         }
     }
+    // a sharded step: the last CTA publishes this GPU's loss partial and signals the peers (reg_shard.cuh)
     if (a.shard.G > 0) shard_pair_kernel_tail(a, reinterpret_cast<acc_t *>(stage));
 }
 
@@ -1032,7 +1035,9 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
         rc = run_chunk_sort(spec, P.R, P.B, 0, dest, nullptr, st);
         if (rc) return rc;
         timeline_mark(st, "sort");
-        rc = launch_runs_merge(rs, P.R, L.Bpad, cabs, Xs, As, Es, perm, flags, nullptr, 0, 0, 0, st);
+        PosDest pd;
+        memset(&pd, 0, sizeof(pd));  // one GPU: the merge places the elements itself
+        rc = launch_runs_merge(rs, P.R, L.Bpad, cabs, Xs, As, Es, perm, flags, nullptr, 0, 0, 0, pd, 0, -1, st);
         if (rc) return rc;
         timeline_mark(st, "merge");
     } else {

@@ -131,7 +131,8 @@ class LocalShardGroup:
     """G virtual ranks of the sharded step inside ONE process on ONE device (tests, and timing one rank's share of a
     G-GPU step on a single GPU).  The ranks' communication buffers are plain device memory of the same process; since
     a rank's wait could never be satisfied by a kernel queued behind it on the same stream, the step is driven
-    phase by phase: publish for every rank, then merge + pairs for every rank, then finalize for every rank."""
+    phase by phase: sort + publish for every rank, then ranking of the own runs for every rank, then apply + plan +
+    pairs for every rank, then finalize for every rank."""
 
     def __init__(self, world: int, n_cap: int, R_cap: int, device="cuda"):
         device = torch.device(device)
@@ -148,7 +149,7 @@ class LocalShardGroup:
         """z_parts[g] / label_parts[g]: rank g's rows.  Returns [(loss64, loss32, grad_cols)] per rank."""
         n_all = [int(z.shape[0]) for z in z_parts]
         outs = [None] * self.world
-        for phase in (1, 2, 4):
+        for phase in (1, 2, 4, 8):
             for g, h in enumerate(self.ranks):
                 outs[g] = h.step(z_parts[g], label_parts[g], reg_dims, label_cols, n_all, gamma, factor, want_grad, phase)
         return outs

@@ -9,9 +9,11 @@ epilogue + gradient scatter (loss and dL/dz both produced).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-N>1 is strong scaling of the same global batch: each rank owns B/N rows (its own samples), the
-packed columns are all-gathered over NCCL, each rank sweeps its rows against all columns and one
-float64 loss partial is all-reduced (arvae_b200/distributed.py).
+N>1 is strong scaling of the same global batch: each rank owns B/N rows (its own samples); the exchange
+is done by the kernels themselves over NVLink peer memory (arvae_b200.distributed.ShardComm, csrc/reg_shard.cuh):
+per-rank sort, sorted runs stored into every peer, merge, 1/N of the single-GPU plan swept per rank, row sums and
+loss partials pulled from peers.  No NCCL call inside a step (--transport nccl selects the all-gather / all-reduce
+form instead).
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -204,6 +206,8 @@ def main():
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 dense, 2 sorted")
     ap.add_argument("--batch", type=int, default=0, help="override B (parity/scaling sweeps; 0 = config C4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="nvlink", choices=["nvlink", "nccl"],
+                    help="N>1: nvlink = peer-memory exchange inside the kernels (ShardComm); nccl = all-gather + all-reduce")
     ap.add_argument("--graph", type=int, default=0,
                     help="1: replay the single-GPU device-resident step as CUDA graphs (measured: no gain at C4, and the "
                          "library's per-kernel timing hooks and launch counter do not see replays); default 0 = eager")
@@ -246,6 +250,11 @@ def main():
     lab_dev = lab_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    comm = None
+    if world > 1 and args.transport == "nvlink":
+        comm = adist.ShardComm(n_local, R)
+    n_all = _lib.i64_array([n_local] * world)
+
     graphed = None
     if args.graph and world == 1:  # (capturing the NCCL collectives of the sharded step deadlocked here: not offered)
         try:
@@ -263,7 +272,7 @@ def main():
         elif world == 1:
             loss = arvae_b200.reg_loss_fused(z, lab_dev, dims, gamma, delta, algo=args.algo)
         else:
-            loss = adist.reg_loss_sharded(z, lab_dev, dims, gamma, delta, algo=args.algo)
+            loss = adist.reg_loss_sharded(z, lab_dev, dims, gamma, delta, algo=args.algo, comm=comm)
         loss.backward()
         return loss, z.grad
 
@@ -281,6 +290,15 @@ def main():
                                              ctypes.c_void_p(grad_host.data_ptr()),
                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             _lib.check(rc, "arvae_reg_loss_host_f32")
+            return loss_c.value
+        if comm is not None:
+            loss_c = ctypes.c_float()
+            rc = lib.arvae_shard_reg_loss_host_f32(comm.h.ctx, ctypes.c_void_p(z_host.data_ptr()), Z,
+                                                   ctypes.c_void_p(lab_host.data_ptr()), A, _lib.i32_array(dims),
+                                                   _lib.i32_array(dims), R, n_all, gamma, delta, ctypes.byref(loss_c),
+                                                   ctypes.c_void_p(grad_host.data_ptr()),
+                                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            _lib.check(rc, "arvae_shard_reg_loss_host_f32")
             return loss_c.value
         z = z_host.to(dev, non_blocking=True).requires_grad_(True)
         lab = lab_host.to(dev, non_blocking=True)
@@ -357,6 +375,8 @@ def main():
     h2d = z_host.numel() * 4 + lab_host.numel() * 4
     d2h = grad_host.numel() * 4 + 4
 
+    if comm is not None:
+        comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -412,6 +432,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "B": B, "Z": Z, "R": R, "gamma": gamma, "delta": delta,
                    "pairs_per_step": pairs, "parallelism": f"row-block x{world}" if world > 1 else "single GPU",
+                   "transport": (args.transport if world > 1 else None),
                    "algo": args.algo, "cuda_graph": graphed is not None,
                    "l2_flush": "256 MiB memset between the timed steps (each step has its own CUDA event pair; the "
                                "flush is outside the per-step intervals; inputs are ~6 MB, far below L2)",

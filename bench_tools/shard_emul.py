@@ -2,9 +2,9 @@
 """One rank's share of a G-GPU sharded step, timed on ONE GPU.
 
 G virtual ranks of the NVLink-sharded step (arvae_b200.distributed.LocalShardGroup) run in one process; the step is
-driven phase by phase (A publish, B merge + plan + pair kernel, C finalize) for every rank, and the phases of ONE rank
+driven phase by phase (A sort + publish, B rank own runs, C apply + plan + pair kernel, D finalize) for every rank, and the phases of ONE rank
 are bracketed with CUDA events.  What a real rank executes is exactly A + B + C of its own (plus NVLink latency and
-the wait for the slowest peer), so max(A) + max(B) + max(C) is the device time a G-GPU step needs per rank -- the
+the wait for the slowest peer), so max(A) + max(B) + max(C) + max(D) is the device time a G-GPU step needs per rank -- the
 fixed costs of the multi-GPU path can be tuned on a 1-GPU box.
 
     python bench_tools/shard_emul.py [--world 8] [--batch 65536] [--steps 20]
@@ -46,22 +46,22 @@ def main():
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    times = {1: [], 2: [], 4: []}
+    times = {1: [], 2: [], 4: [], 8: []}
     pair_ms = []
     for it in range(args.steps + 3):
-        for phase in (1, 2, 4):
+        for phase in (1, 2, 4, 8):
             rec = []
             for g, h in enumerate(grp.ranks):
                 if g == 0:
                     flush.zero_()
-                    if phase == 2:
+                    if phase == 4:
                         lib.arvae_profile_enable(1)
                 e0, e1 = ev(), ev()
                 e0.record()
                 h.step(zp[g], lp[g], dims, dims, n_all, c["gamma"], c["delta"], True, phase)
                 e1.record()
                 rec.append((e0, e1))
-                if g == 0 and phase == 2:
+                if g == 0 and phase == 4:
                     import ctypes
                     ks, kn = ctypes.c_float(), ctypes.c_int()
                     lib.arvae_profile_pair_kernel_ms(ctypes.byref(ks), ctypes.byref(kn))
@@ -87,7 +87,7 @@ def main():
     buf = ctypes.create_string_buffer(4096)
     tl = {}
     for it in range(5):
-        for phase in (1, 2, 4):
+        for phase in (1, 2, 4, 8):
             for g, h in enumerate(grp.ranks):
                 if g == 0:
                     lib.arvae_timeline_enable(1)
@@ -125,10 +125,10 @@ def main():
         cta = {"n": int(len(t)), "start_spread_us": float(st.max()), "end_min_p10_med_p90_max_us": [float(en.min()), float(np.percentile(en, 10)), float(np.median(en)), float(np.percentile(en, 90)), float(en.max())],
                "mean_busy_us": float(np.mean(en - st))}
     med = {k: statistics.median(v) for k, v in times.items()}
-    out = {"world": G, "B": B, "rank0_publish_ms": med[1], "rank0_merge_plan_pair_ms": med[2], "rank0_finalize_ms": med[4],
+    out = {"world": G, "B": B, "rank0_publish_ms": med[1], "rank0_rank_own_ms": med[2], "rank0_apply_plan_pair_ms": med[4], "rank0_finalize_ms": med[8],
            "rank0_pair_kernel_ms": statistics.median(pair_ms) if pair_ms else None,
-           "rank0_step_ms": med[1] + med[2] + med[4], "single_gpu_fwd_ms": statistics.median(single),
-           "fixed_ms": med[1] + med[2] + med[4] - (statistics.median(pair_ms) if pair_ms else 0.0),
+           "rank0_step_ms": med[1] + med[2] + med[4] + med[8], "single_gpu_fwd_ms": statistics.median(single),
+           "fixed_ms": med[1] + med[2] + med[4] + med[8] - (statistics.median(pair_ms) if pair_ms else 0.0),
            "rank0_timeline_us": timeline, "single_gpu_timeline_us": timeline1, "rank0_cta_times": cta,
            "note": "flushed L2 before every timed phase; events bracket the launches of rank 0 only (cold start of each phase)"}
     print(json.dumps(out))

@@ -198,8 +198,9 @@ ARVAE_API int arvae_pack_columns_f32(const float *z_dev, int64_t z_row_stride, i
  *   arvae_shard_reg_loss_f32  one step.  z_local_dev / labels_local_dev hold THIS rank's n_all_host[rank] rows;
  *                             loss_out_dev [1] double (+ optional float) receives the GLOBAL loss on every rank,
  *                             grad_cols_out_dev [n_local, R] the gradient columns of this rank's rows (NULL: loss only).
- *                             `phases` = 0 runs the whole step; bits 1 | 2 | 4 run only publish / merge+pairs /
- *                             finalize (tests drive several ranks of one process through the phases in lockstep).
+ *                             `phases` = 0 runs the whole step; bits 1 | 2 | 4 | 8 run only sort+publish / rank own
+ *                             runs / apply+plan+pairs / finalize (tests drive several ranks of one process through
+ *                             the phases in lockstep).
  *                             Stream-ordered, no host sync, no NCCL.  A peer that never shows up makes the loss NaN
  *                             after a bounded wait (arvae_shard_status reports it) instead of hanging the GPU.
  *   arvae_shard_reg_loss_host_f32  the same with HOST buffers in and out (H2D, step, dL/dz scatter, D2H, sync).

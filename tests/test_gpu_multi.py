@@ -1,8 +1,10 @@
-"""Row-block sharding on real GPUs (needs >= 2 devices; skipped otherwise): every world size gives
-the single-GPU loss and gradient.  On the dense path (B < 8192) each rank's gradient rows are BITWISE
-identical to the same rows of the single-GPU run (each row is owned by one rank and sweeps the same
-columns in the same order); on the attribute-sorted path the row tiles differ per partition, so
-equality holds to fp32 rounding (2e-6 of the column max)."""
+"""Row-block sharding on real GPUs, one process per GPU (needs >= 2 devices; skipped otherwise): every world size
+gives the single-GPU loss and gradient.
+
+transport "nvlink" (ShardComm, csrc/reg_shard.cuh): loss and every gradient element BITWISE equal to the single-GPU
+sorted-path result, for every world size and over several steps of one communicator (SURVEY section 8e's check).
+transport "nccl": on the dense path (B < 8192) gradient rows are bitwise those of the single-GPU run; on the
+attribute-sorted path equality holds to the fixed-point quantum of the row sums."""
 import os
 import sys
 
@@ -16,7 +18,7 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, B, q):
+def _worker(rank, world, port, B, transport, q):
     sys.path.insert(0, REPO)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -28,10 +30,16 @@ def _worker(rank, world, port, B, q):
         n = B // world
         z_local = c["z"][rank * n:(rank + 1) * n].cuda().requires_grad_(True)
         lab_local = c["labels"][rank * n:(rank + 1) * n].cuda()
-        loss = adist.reg_loss_sharded(z_local, lab_local, c["reg_dims"], c["gamma"], c["delta"])
-        loss.backward()
+        comm = adist.ShardComm(n, len(c["reg_dims"])) if transport == "nvlink" else None
+        for step in range(3 if comm is not None else 1):  # several steps through one communicator: epochs, buffer reuse
+            z_local.grad = None
+            loss = adist.reg_loss_sharded(z_local, lab_local, c["reg_dims"], c["gamma"], c["delta"], comm=comm)
+            loss.backward()
         torch.cuda.synchronize()
-        q.put((rank, float(loss), z_local.grad.cpu().numpy()))
+        status = comm.h.status() if comm is not None else (0, 0)
+        q.put((rank, float(loss), z_local.grad.cpu().numpy(), status))
+        if comm is not None:
+            comm.close()
     finally:
         dist.destroy_process_group()
 
@@ -39,15 +47,16 @@ def _worker(rank, world, port, B, q):
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("B", [4096, 16384])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_equals_single_gpu(world, B):
+@pytest.mark.parametrize("transport", ["nvlink", "nccl"])
+def test_sharded_equals_single_gpu(world, B, transport):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import arvae_b200
     from arvae_b200 import synth
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + world + (B // 4096)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, B, q)) for r in range(world)]
+    port = 29700 + (os.getpid() % 1000) + world + (B // 4096) + (100 if transport == "nccl" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, B, transport, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = sorted((q.get(timeout=240) for _ in range(world)), key=lambda t: t[0])
@@ -56,14 +65,19 @@ def test_sharded_equals_single_gpu(world, B):
         assert p.exitcode == 0
     c = synth.make_case("c4_mnist_b65536", B=B)
     z = c["z"].cuda().requires_grad_(True)
-    loss = arvae_b200.reg_loss_fused(z, c["labels"].cuda(), c["reg_dims"], c["gamma"], c["delta"])
+    algo = arvae_b200.ALGO_SORTED if transport == "nvlink" else arvae_b200.ALGO_AUTO
+    loss = arvae_b200.reg_loss_fused(z, c["labels"].cuda(), c["reg_dims"], c["gamma"], c["delta"], algo=algo)
     loss.backward()
     for r in results:
         assert r[1] == results[0][1]
         assert abs(r[1] - loss.item()) <= 1e-6 * abs(loss.item())
     got = np.concatenate([r[2] for r in results], axis=0)
     ref = z.grad.cpu().numpy()
-    if B < 8192:
+    if transport == "nvlink":
+        assert all(r[3] == (0, 3) for r in results), [r[3] for r in results]  # no wait gave up; three epochs
+        assert all(r[1] == loss.item() for r in results)
+        assert np.array_equal(got, ref)
+    elif B < 8192:
         assert np.array_equal(got, ref)
     else:
         scale = np.abs(ref).max(axis=0) + 1e-30
