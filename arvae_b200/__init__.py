@@ -10,14 +10,14 @@ from . import _lib  # noqa: F401
 from . import graphs  # noqa: F401
 from . import music  # noqa: F401
 from . import evaluation  # noqa: F401
-from .ops import (ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, ALGO_TRIANGLE, compute_kld_loss, compute_reg_loss, latent_head, mufu_per_pair,
+from .ops import (ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, ALGO_TRIANGLE, compute_kld_loss, compute_reg_loss, latent_head, latent_loss_head, mufu_per_pair,
                   reg_loss_fused, reg_loss_rows, reg_loss_sign, reparam_kld_reg, reparametrize, sign_matrix,
                   attr_argsort, pack_columns)
 
 __version__ = "0.1.0"
 
 __all__ = ["compute_reg_loss", "reg_loss_sign", "reg_loss_fused", "reg_loss_rows", "compute_kld_loss",
-           "reparametrize", "latent_head", "reparam_kld_reg", "sign_matrix", "install", "uninstall",
+           "reparametrize", "latent_head", "latent_loss_head", "reparam_kld_reg", "sign_matrix", "install", "uninstall",
            "ALGO_AUTO", "ALGO_DENSE", "ALGO_SORTED", "ALGO_TRIANGLE", "mufu_per_pair", "attr_argsort", "pack_columns", "graphs", "music", "evaluation"]
 
 _saved = {}

@@ -40,6 +40,11 @@ SIGNATURES = {
                                                  _vp, _sz, _vp]),
     "arvae_latent_head_bwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i32p, _i32, _f, _vp, _vp,
                                                  _i64, _i64, _vp, _vp, _vp]),
+    "arvae_head_fused_workspace_bytes": (_sz, [_i64, _i32]),
+    "arvae_head_fused_fwd_f32": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i64, _vp, _i64, _i64, _c_i32p, _c_i32p, _i32,
+                                                _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "arvae_head_fused_bwd_f32": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _c_i32p, _i32, _vp, _vp, _i64, _i64,
+                                                _vp, _vp, _vp]),
     "arvae_reg_loss_host_f32": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _c_i32p, _c_i32p, _i32, _f, _f,
                                                _i32, _vp, _vp, _vp]),
     "arvae_host_release": (None, []),

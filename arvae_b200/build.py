@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("ARVAE_LIB_OUT") or os.path.join(CSRC, "libarvae_b200.so")  # override: A/B experiments
-SOURCES = ["api.cu", "reg_dense.cu", "reg_sorted.cu", "sort.cu", "latent_head.cu", "music_attrs.cu", "eval_metrics.cu"]
+SOURCES = ["api.cu", "reg_dense.cu", "reg_sorted.cu", "sort.cu", "latent_head.cu", "head_fused.cu", "music_attrs.cu", "eval_metrics.cu"]
 HEADERS = ["common.cuh", "reg_internal.cuh", os.path.join("..", "..", "include", "arvae_b200.h")]
 
 NVCC_FLAGS = [
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC"]
+           "-Xcompiler", "-fPIC", "-ldl"]  # -ldl: NVTX v3 loads its tool backend with dlopen
     p = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if p.returncode != 0:
         raise RuntimeError("link failed:\n" + p.stdout + p.stderr)

@@ -220,6 +220,7 @@ int arvae_reg_loss_fwdbwd_f32(const float *z_dev, int64_t z_row_stride, int64_t 
                               int32_t algo, double *loss_out_dev, float *loss_f32_out_dev,
                               float *grad_cols_out_dev, double *row_loss_out_dev, int32_t *row_sign_out_dev,
                               void *workspace_dev, size_t workspace_bytes, void *stream) {
+    NvtxRange nvtx_range("arvae_reg_loss_fwdbwd_f32");
     RegProblem P;
     int rc = fill_dims(P.dims, reg_dims_host, label_cols_host, R);
     if (rc) return rc;
@@ -299,6 +300,7 @@ int arvae_reg_loss_scatter_bwd_f32(const float *grad_cols_dev, const float *grad
                                    const int32_t *reg_dims_host, int32_t R, int64_t n_rows,
                                    int64_t Z, float *grad_z_dev, int64_t gz_row_stride,
                                    void *stream) {
+    NvtxRange nvtx_range("arvae_reg_loss_scatter_bwd_f32");
     RegDims d;
     int rc = fill_dims(d, reg_dims_host, nullptr, R);
     if (rc) return rc;
@@ -325,6 +327,7 @@ int arvae_latent_head_fwd_f32(const float *loc_dev, const float *scale_dev, cons
                               double *kld_sum_out_dev, float *kld_mean_out_dev,
                               float *kld_loss_out_dev, float *kcoef_out_dev, void *ws_dev,
                               size_t ws_bytes, void *stream) {
+    NvtxRange nvtx_range("arvae_latent_head_fwd_f32");
     if (B < 0 || Z < 0 || !kld_sum_out_dev || !ws_dev ||
         (B * Z > 0 && (!loc_dev || !scale_dev || !eps_dev || !z_out_dev))) {
         set_error("bad argument to latent_head_fwd");
@@ -341,6 +344,7 @@ int arvae_latent_head_bwd_f32(const float *loc_dev, const float *scale_dev, cons
                               float kscale, const float *kcoef_dev, const float *gkld_dev,
                               int64_t B, int64_t Z, float *dloc_dev, float *dscale_dev,
                               void *stream) {
+    NvtxRange nvtx_range("arvae_latent_head_bwd_f32");
     RegDims d;
     int rc = fill_dims(d, reg_dims_host, nullptr, grad_cols_dev ? R : 0);
     if (rc) return rc;
@@ -353,11 +357,59 @@ int arvae_latent_head_bwd_f32(const float *loc_dev, const float *scale_dev, cons
                                dscale_dev, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t arvae_head_fused_workspace_bytes(int64_t B, int32_t R) { return head_fused_ws_bytes(B, R); }
+
+int arvae_head_fused_fwd_f32(const float *loc_dev, const float *sd_dev, int32_t sd_is_log_std, const float *eps_dev,
+                             int64_t B, int64_t Z, const float *labels_dev, int64_t lab_row_stride,
+                             int64_t lab_col_stride, const int32_t *reg_dims_host, const int32_t *label_cols_host,
+                             int32_t R, float beta, float capacity, float gamma, float factor, float *z_out_dev,
+                             float *scale_out_dev, float *kld_mean_out_dev, float *kld_loss_out_dev,
+                             float *kcoef_out_dev, float *reg_loss_out_dev, float *grad_cols_out_dev,
+                             void *workspace_dev, size_t workspace_bytes, void *stream) {
+    NvtxRange nvtx_range("arvae_head_fused_fwd_f32");
+    RegDims d;
+    int rc = fill_dims(d, reg_dims_host, label_cols_host, R);
+    if (rc) return rc;
+    if (R < 1 || Z < 1 || !loc_dev || !sd_dev || !eps_dev || !labels_dev || !z_out_dev || !reg_loss_out_dev ||
+        !workspace_dev) {
+        set_error("bad argument to head_fused_fwd (needs R >= 1 and non-null loc / sd / eps / labels / z_out / reg_loss_out / workspace)");
+        return ARVAE_E_BADARG;
+    }
+    for (int r = 0; r < R; ++r)
+        if (d.zcol[r] >= Z) {
+            set_error("reg dim %d out of range for Z=%lld", d.zcol[r], (long long)Z);
+            return ARVAE_E_BADARG;
+        }
+    return run_head_fused_fwd(loc_dev, sd_dev, sd_is_log_std, eps_dev, B, Z, labels_dev, lab_row_stride, lab_col_stride, d,
+                              R, beta, capacity, gamma, factor, z_out_dev, scale_out_dev, kld_mean_out_dev,
+                              kld_loss_out_dev, kcoef_out_dev, reg_loss_out_dev, grad_cols_out_dev,
+                              reinterpret_cast<char *>(workspace_dev), workspace_bytes,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int arvae_head_fused_bwd_f32(const float *loc_dev, const float *sd_dev, int32_t sd_is_log_std, const float *eps_dev,
+                             const float *dz_up_dev, const float *grad_cols_dev, const float *greg_dev,
+                             const int32_t *reg_dims_host, int32_t R, const float *kcoef_dev, const float *gkld_dev,
+                             int64_t B, int64_t Z, float *dloc_dev, float *dsd_dev, void *stream) {
+    NvtxRange nvtx_range("arvae_head_fused_bwd_f32");
+    RegDims d;
+    int rc = fill_dims(d, reg_dims_host, nullptr, grad_cols_dev ? R : 0);
+    if (rc) return rc;
+    if (B < 0 || Z < 0 || (B * Z > 0 && (!loc_dev || !sd_dev || !eps_dev))) {
+        set_error("bad argument to head_fused_bwd");
+        return ARVAE_E_BADARG;
+    }
+    return run_latent_head_bwd(loc_dev, sd_dev, eps_dev, dz_up_dev, grad_cols_dev, greg_dev, d, grad_cols_dev ? R : 0, 1.0f,
+                               kcoef_dev, gkld_dev, B, Z, dloc_dev, dsd_dev, reinterpret_cast<cudaStream_t>(stream),
+                               sd_is_log_std ? 1 : 0);
+}
+
 int arvae_reg_loss_host_f32(const float *z_host, int64_t B, int64_t Z, const float *labels_host,
                             int64_t A, const int32_t *reg_dims_host,
                             const int32_t *label_cols_host, int32_t R, float gamma, float factor,
                             int32_t algo, float *loss_out_host, float *grad_z_out_host,
                             void *stream) {
+    NvtxRange nvtx_range("arvae_reg_loss_host_f32");
     if (B < 0 || Z <= 0 || A <= 0 || !loss_out_host || (B > 0 && (!z_host || !labels_host))) {
         set_error("bad argument to reg_loss_host");
         return ARVAE_E_BADARG;
@@ -429,6 +481,7 @@ int arvae_pack_columns_f32(const float *z_dev, int64_t z_row_stride, int64_t z_c
                            const float *labels_dev, int64_t lab_row_stride, int64_t lab_col_stride,
                            const int32_t *reg_dims_host, const int32_t *label_cols_host, int32_t R,
                            int64_t n_rows, float *out_dev, void *stream) {
+    NvtxRange nvtx_range("arvae_pack_columns_f32");
     RegDims d;
     int rc = fill_dims(d, reg_dims_host, label_cols_host, R);
     if (rc) return rc;
@@ -447,6 +500,7 @@ size_t arvae_attr_argsort_workspace_bytes(int64_t B) {
 
 int arvae_attr_argsort_f32(const float *labels_dev, int64_t lab_stride, int64_t B, int32_t *perm_out_dev,
                            void *workspace_dev, size_t workspace_bytes, void *stream) {
+    NvtxRange nvtx_range("arvae_attr_argsort_f32");
     if (B < 0 || !workspace_dev || (B > 0 && (!labels_dev || !perm_out_dev))) {
         set_error("bad argument to attr_argsort");
         return ARVAE_E_BADARG;
@@ -467,6 +521,7 @@ int arvae_attr_argsort_f32(const float *labels_dev, int64_t lab_stride, int64_t 
 int arvae_measure_attributes_i64(const int64_t *measures_dev, int64_t B, int64_t T, int64_t row_stride,
                                  const int32_t *lut_dev, int64_t V, const float *rhy_weights_dev, float *out_dev,
                                  void *stream) {
+    NvtxRange nvtx_range("arvae_measure_attributes_i64");
     if (B < 0 || T <= 0 || V <= 0 || (B > 0 && (!measures_dev || !lut_dev || !rhy_weights_dev || !out_dev))) {
         set_error("bad argument to measure_attributes");
         return ARVAE_E_BADARG;
@@ -485,6 +540,7 @@ int arvae_eval_metrics_f32(const float *codes_dev, int64_t codes_row_stride, int
                            int32_t Z, int32_t A, double *rho_out_dev, double *pval_out_dev, double *corr_out_dev,
                            double *sap_out_dev, double *scores_out_dev, void *workspace_dev, size_t workspace_bytes,
                            void *stream) {
+    NvtxRange nvtx_range("arvae_eval_metrics_f32");
     if (B < 1 || B > 0x7fffffffLL || Z < 1 || A < 1 || Z > kEvalMaxCodes || A > kEvalMaxAttrs) {
         set_error("eval_metrics: need 1 <= B < 2^31, 1 <= Z <= %d, 1 <= A <= %d (got B=%lld Z=%d A=%d)", kEvalMaxCodes,
                   kEvalMaxAttrs, (long long)B, (int)Z, (int)A);
@@ -608,6 +664,7 @@ int arvae_shard_reg_loss_f32(void *ctx, const float *z_local_dev, int64_t z_row_
                              const int32_t *reg_dims_host, const int32_t *label_cols_host, int32_t R,
                              const int64_t *n_all_host, float gamma, float factor, double *loss_out_dev,
                              float *loss_f32_out_dev, float *grad_cols_out_dev, int32_t phases, void *stream) {
+    NvtxRange nvtx_range("arvae_shard_reg_loss_f32");
     ShardCtx *C = as_ctx(ctx);
     ShardStep S;
     int rc = shard_fill_step(C, S, reg_dims_host, label_cols_host, R, n_all_host);
@@ -628,6 +685,7 @@ int arvae_shard_reg_loss_host_f32(void *ctx, const float *z_local_host, int64_t 
                                   int64_t A, const int32_t *reg_dims_host, const int32_t *label_cols_host, int32_t R,
                                   const int64_t *n_all_host, float gamma, float factor, float *loss_out_host,
                                   float *grad_z_out_host, void *stream) {
+    NvtxRange nvtx_range("arvae_shard_reg_loss_host_f32");
     ShardCtx *C = as_ctx(ctx);
     ShardStep S;
     int rc = shard_fill_step(C, S, reg_dims_host, label_cols_host, R, n_all_host);

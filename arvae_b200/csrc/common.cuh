@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -18,6 +19,15 @@ void profile_begin(cudaStream_t st);
 void profile_end(cudaStream_t st);
 // named CUDA-event marks between the launches of a step (no-ops unless arvae_timeline_enable(1)); experiments only
 void timeline_mark(cudaStream_t st, const char *name);
+
+// NVTX range around a public entry point (visible in Nsight Systems / Compute timelines; a no-op costing one
+// pointer test when no tool is attached -- NVTX v3 is header-only and loads its backend lazily).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 #define ARVAE_CUDA_TRY(expr)                                        \
     do {                                                            \

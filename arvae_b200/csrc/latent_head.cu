@@ -76,7 +76,7 @@ latent_head_bwd_kernel(const float *__restrict__ loc, const float *__restrict__ 
                        const float *__restrict__ grad_cols, const float *__restrict__ greg,
                        RegDims dims, int R, float kscale, const float *__restrict__ kcoef,
                        const float *__restrict__ gkld, int64_t B, int64_t Z,
-                       float *__restrict__ dloc, float *__restrict__ dscale) {
+                       float *__restrict__ dloc, float *__restrict__ dscale, int sd_is_log) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B * Z) return;
     const int64_t b = e / Z;
@@ -90,9 +90,13 @@ latent_head_bwd_kernel(const float *__restrict__ loc, const float *__restrict__ 
         dz = fmaf(g, v, dz);
     }
     const float k = kscale * (kcoef ? __ldg(kcoef) : 1.0f) * (gkld ? __ldg(gkld) : 1.0f);
-    const float s = scale[e];
+    // sd_is_log: `scale` holds log_std and `dscale` receives d/d(log_std) = d/d(scale) * scale
+    const float s = sd_is_log ? expf(scale[e]) : scale[e];
     if (dloc) dloc[e] = dz + k * loc[e];
-    if (dscale) dscale[e] = dz * eps[e] + k * (s - 1.0f / s);
+    if (dscale) {
+        const float ds = dz * eps[e] + k * (s - 1.0f / s);
+        dscale[e] = sd_is_log ? ds * s : ds;
+    }
 }
 
 size_t latent_head_ws_bytes(int64_t B, int64_t Z) {
@@ -122,11 +126,11 @@ int run_latent_head_fwd(const float *loc, const float *scale, const float *eps, 
 int run_latent_head_bwd(const float *loc, const float *scale, const float *eps, const float *dz_up,
                         const float *grad_cols, const float *greg, const RegDims &dims, int R,
                         float kscale, const float *kcoef, const float *gkld, int64_t B, int64_t Z,
-                        float *dloc, float *dscale, cudaStream_t st) {
+                        float *dloc, float *dscale, cudaStream_t st, int sd_is_log) {
     const int64_t n = B * Z;
     if (n <= 0) return 0;
     latent_head_bwd_kernel<<<(unsigned)ceil_div(n, kHeadThreads), kHeadThreads, 0, st>>>(
-        loc, scale, eps, dz_up, grad_cols, greg, dims, R, kscale, kcoef, gkld, B, Z, dloc, dscale);
+        loc, scale, eps, dz_up, grad_cols, greg, dims, R, kscale, kcoef, gkld, B, Z, dloc, dscale, sd_is_log);
     ARVAE_LAUNCH_CHECK("latent_head_bwd_kernel");
     return 0;
 }

@@ -41,35 +41,7 @@ pack_columns_kernel(const float *__restrict__ z, int64_t zrs, int64_t zcs,
 // ------------------------------------------------------------------------------------------------
 // the pair loop
 // ------------------------------------------------------------------------------------------------
-// One pair.  With xs = sgn(f) x:  d = xs_i - xs_j (exact sign of t), r = 1/(1+2^(|c| d)) = (1 - t)/2
-//   =>  t = 1 - 2r,  1 - t^2 = 4 (r - r^2),  v = t - s = (1 - s) - 2r
-//   loss += |v| ;  grad += sgn(v) * (r - r^2)          (x4 applied at the end)
-// sgn(v) with sgn(0) = 0, as abs-backward has it: for s != 0 it is -s (or the factor (r - r^2) is
-// 0); for a tie it is sgn(t) = sgn(d), which MUST come from d itself -- near d = 0 the MUFU
-// approximations cannot be trusted for the sign of 1 - 2r, and (1 - t^2) is at its maximum there.
-//   q = -s * 2^127 + d * 2^60 ;  sgn = clamp(q, -1, 1)
-// is exact whenever |d| >= 2^-60 or d == 0 (d * 2^60 only outweighs 2^127 when tanh is saturated
-// and the factor is 0 anyway).
-template <bool GRAD, bool SIGNS = false>
-__device__ __forceinline__ void pair_general(float xi, float ai, float xj, float aj, float cabs,
-                                             float &lacc, float &gacc, float *kacc = nullptr) {
-    const float d = xi - xj;
-    const float e = ex2_approx(d * cabs);
-    const float r = rcp_approx(e + 1.0f);
-    const float gt = ai > aj ? 1.0f : 0.0f;
-    const float lt = ai < aj ? 1.0f : 0.0f;
-    const float k = (1.0f - gt) + lt;  // 1 - s  in {0,1,2}
-    const float v = fmaf(-2.0f, r, k);
-    lacc += fabsf(v);
-    if (SIGNS) *kacc += k;  // small integers: exact
-    if (GRAD) {
-        const float w4 = fmaf(-r, r, r);
-        const float q = fmaf(k - 1.0f, 1.7014118e38f, d * 1.1529215e18f);
-        const float sg = fminf(fmaxf(q, -1.0f), 1.0f);
-        gacc = fmaf(sg, w4, gacc);
-    }
-}
-
+// (the per-pair arithmetic, pair_general, lives in reg_internal.cuh: head_fused.cu sweeps with it too)
 template <int RI, bool GRAD, bool SIGNS>
 __global__ void __launch_bounds__(kDenseThreads)
 reg_dense_kernel(const float *__restrict__ U, const float *__restrict__ A, float cabs, int64_t Bpad,

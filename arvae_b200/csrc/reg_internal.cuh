@@ -44,12 +44,46 @@ struct DenseLayout {
     size_t off_U, off_A, off_pgrad, off_prow, off_lossp, off_psign, bytes;
 };
 
+// One pair.  With xs = sgn(f) x:  d = xs_i - xs_j (exact sign of t), r = 1/(1+2^(|c| d)) = (1 - t)/2
+//   =>  t = 1 - 2r,  1 - t^2 = 4 (r - r^2),  v = t - s = (1 - s) - 2r
+//   loss += |v| ;  grad += sgn(v) * (r - r^2)          (x4 applied at the end)
+// sgn(v) with sgn(0) = 0, as abs-backward has it: for s != 0 it is -s (or the factor (r - r^2) is
+// 0); for a tie it is sgn(t) = sgn(d), which MUST come from d itself -- near d = 0 the MUFU
+// approximations cannot be trusted for the sign of 1 - 2r, and (1 - t^2) is at its maximum there.
+//   q = -s * 2^127 + d * 2^60 ;  sgn = clamp(q, -1, 1)
+// is exact whenever |d| >= 2^-60 or d == 0 (d * 2^60 only outweighs 2^127 when tanh is saturated
+// and the factor is 0 anyway).
+template <bool GRAD, bool SIGNS = false>
+__device__ __forceinline__ void pair_general(float xi, float ai, float xj, float aj, float cabs,
+                                             float &lacc, float &gacc, float *kacc = nullptr) {
+    const float d = xi - xj;
+    const float e = ex2_approx(d * cabs);
+    const float r = rcp_approx(e + 1.0f);
+    const float gt = ai > aj ? 1.0f : 0.0f;
+    const float lt = ai < aj ? 1.0f : 0.0f;
+    const float k = (1.0f - gt) + lt;  // 1 - s  in {0,1,2}
+    const float v = fmaf(-2.0f, r, k);
+    lacc += fabsf(v);
+    if (SIGNS) *kacc += k;  // small integers: exact
+    if (GRAD) {
+        const float w4 = fmaf(-r, r, r);
+        const float q = fmaf(k - 1.0f, 1.7014118e38f, d * 1.1529215e18f);
+        const float sg = fminf(fmaxf(q, -1.0f), 1.0f);
+        gacc = fmaf(sg, w4, gacc);
+    }
+}
+
 DenseLayout dense_layout(int64_t B_total, int64_t n_rows, int R, int sm_count);
 int run_reg_dense(const RegProblem &P, const DenseLayout &L, char *ws, cudaStream_t st);
 int run_scatter_bwd(const float *grad_cols, const float *grad_out, const RegDims &dims, int R,
                     int64_t n_rows, int64_t Z, float *grad_z, int64_t gzrs, cudaStream_t st);
 int run_pack_slice(const float *z, int64_t zrs, int64_t zcs, const float *lab, int64_t lrs, int64_t lcs,
                    const RegDims &dims, int R, int64_t n_rows, float *out, cudaStream_t st);
+size_t head_fused_ws_bytes(int64_t B, int R);
+int run_head_fused_fwd(const float *loc, const float *sd, int sd_is_log, const float *eps, int64_t B, int64_t Z,
+                       const float *lab, int64_t lrs, int64_t lcs, const RegDims &dims, int R, float beta, float capacity,
+                       float gamma, float factor, float *z_out, float *scale_out, float *kld_mean_out, float *kld_loss_out,
+                       float *kcoef_out, float *reg_loss_out, float *grad_cols_out, char *ws, size_t ws_bytes, cudaStream_t st);
 int run_extract_perm(const unsigned long long *keys, int64_t B, int32_t *perm, cudaStream_t st);
 int run_sign_matrix(const float *a, int64_t stride, int64_t B, int8_t *out, cudaStream_t st);
 
@@ -198,7 +232,7 @@ int run_latent_head_fwd(const float *loc, const float *scale, const float *eps, 
 int run_latent_head_bwd(const float *loc, const float *scale, const float *eps, const float *dz_up,
                         const float *grad_cols, const float *greg, const RegDims &dims, int R,
                         float kscale, const float *kcoef, const float *gkld, int64_t B, int64_t Z,
-                        float *dloc, float *dscale, cudaStream_t st);
+                        float *dloc, float *dscale, cudaStream_t st, int sd_is_log = 0);
 
 int run_measure_attributes(const long long *measures, int64_t B, int64_t T, int64_t row_stride, const int *lut,
                            int64_t V, const float *weights, float *out, cudaStream_t st);

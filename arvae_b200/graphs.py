@@ -17,11 +17,28 @@ Shapes, reg dims, gamma and factor are baked into the graph (they are constants 
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 from typing import Callable, Sequence
 
 import torch
 
 from . import ops
+
+
+@contextlib.contextmanager
+def quiet_gc():
+    """Collect now and keep the cyclic garbage collector off while a stream is capturing: if it ran during the capture
+    and freed an older CUDA graph / event (graphed callables sit in reference cycles), that free is an operation 'not
+    permitted when stream is capturing' and invalidates the capture (seen as an order-dependent test failure)."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 def graphed_reg_loss(B: int, Z: int, A: int, reg_dims: Sequence[int], gamma: float, factor: float = 1.0,
@@ -34,7 +51,8 @@ def graphed_reg_loss(B: int, Z: int, A: int, reg_dims: Sequence[int], gamma: flo
 
     z0 = torch.randn(B, Z, device=device, requires_grad=True)
     l0 = torch.randn(B, A, device=device)  # labels never get a gradient
-    return torch.cuda.make_graphed_callables(fn, (z0, l0), allow_unused_input=True)
+    with quiet_gc():
+        return torch.cuda.make_graphed_callables(fn, (z0, l0), allow_unused_input=True)
 
 
 def graphed_latent_head(B: int, Z: int, A: int, reg_dims: Sequence[int], beta: float, capacity: float, gamma: float,
@@ -52,5 +70,6 @@ def graphed_latent_head(B: int, Z: int, A: int, reg_dims: Sequence[int], beta: f
     scale = (torch.rand(B, Z, device=device) + 0.5).requires_grad_(True)
     eps = torch.randn(B, Z, device=device)
     lab = torch.randn(B, A, device=device)
-    return torch.cuda.make_graphed_callables(fn, (loc, scale, eps, lab), allow_unused_input=True)
+    with quiet_gc():
+        return torch.cuda.make_graphed_callables(fn, (loc, scale, eps, lab), allow_unused_input=True)
 

@@ -32,8 +32,7 @@ ALGO_AUTO, ALGO_DENSE, ALGO_SORTED, ALGO_TRIANGLE = _lib.ALGO_AUTO, _lib.ALGO_DE
 HAVE_SORTED = True
 HAVE_TRIANGLE = True
 
-_EXACT_IN_F32 = (torch.float32, torch.float16, torch.bfloat16, torch.int8, torch.uint8, torch.int16,
-                 torch.bool)
+_EXACT_IN_F32 = (torch.float32, torch.float16, torch.bfloat16, torch.int8, torch.int16)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -98,6 +97,15 @@ def _prepare_labels(labels: torch.Tensor, label_cols: Sequence[int], B: int, dev
         cols.append(c % A)
     if labels.dtype == torch.float32:
         return labels.detach(), tuple(cols)
+    if labels.dtype == torch.bool:
+        # the reference fails in `a - a.T` (utils/trainer.py:395): same error class, same message
+        raise RuntimeError("Subtraction, the `-` operator, with two bool tensors is not supported. "
+                           "Use the `^` or `logical_xor()` operator instead.")
+    if labels.dtype == torch.uint8:
+        # the reference takes sign() of a WRAPPED uint8 difference (0 or 1, never -1); that is never what a caller
+        # means and no shipped dataset has uint8 labels: refuse rather than silently compute the true sign
+        raise RuntimeError("arvae_b200: uint8 labels are not supported (the reference's uint8 subtraction wraps, so its "
+                           "sign matrix has no -1); cast the labels to a signed or floating type")
     if labels.dtype in _EXACT_IN_F32:
         return labels.detach().to(torch.float32), tuple(cols)
     ranked = torch.stack([_rank_labels(labels.detach()[:, c]) for c in cols], dim=1)
@@ -423,6 +431,75 @@ def _check_head_inputs(loc, scale, eps):
     return loc.contiguous(), scale.contiguous(), eps.detach().contiguous()
 
 
+# ---- the whole head in one launch (csrc/head_fused.cu) -----------------------------------------------
+FUSED_HEAD_MAX_BATCH = 8192
+_fused_ws = {}  # (device index, stream, B, R) -> workspace, zeroed once; every launch leaves it zeroed
+
+
+def _fused_workspace(dev, B: int, R: int) -> torch.Tensor:
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, B, R)
+    ws = _fused_ws.get(key)
+    if ws is None:
+        if len(_fused_ws) > 64:
+            _fused_ws.clear()
+        need = int(_lib.load().arvae_head_fused_workspace_bytes(B, R))
+        ws = _fused_ws[key] = torch.zeros(max(need, 256), dtype=torch.uint8, device=dev)
+    return ws
+
+
+class _HeadFusedFn(torch.autograd.Function):
+    """reparametrize (+ exp(log_std)) + KLD loss + attribute-regularization loss: ONE launch forward, ONE backward."""
+
+    @staticmethod
+    def forward(ctx, loc, sd, eps, labels, reg_dims, label_cols, beta, capacity, gamma, factor, sd_is_log):
+        lib = _lib.load()
+        dev = loc.device
+        B, Z = loc.shape
+        R = len(reg_dims)
+        want_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        with torch.cuda.device(dev):
+            z = torch.empty((B, Z), dtype=torch.float32, device=dev)
+            scale = torch.empty((B, Z), dtype=torch.float32, device=dev) if sd_is_log else None
+            scal = torch.empty(3, dtype=torch.float32, device=dev)  # kld_loss, reg_loss, kcoef
+            grad_cols = torch.empty((B, R), dtype=torch.float32, device=dev) if want_grad else None
+            ws = _fused_workspace(dev, B, R)
+            p = scal.data_ptr()
+            rc = lib.arvae_head_fused_fwd_f32(
+                _ptr(loc), _ptr(sd), 1 if sd_is_log else 0, _ptr(eps), B, Z, _ptr(labels), labels.stride(0),
+                labels.stride(1), _lib.i32_array(reg_dims), _lib.i32_array(label_cols), R, beta, capacity, gamma, factor,
+                _ptr(z), _ptr(scale), None, ctypes.c_void_p(p), ctypes.c_void_p(p + 8), ctypes.c_void_p(p + 4),
+                _ptr(grad_cols), _ptr(ws), ws.numel(), _stream(dev))
+            _lib.check(rc, "arvae_head_fused_fwd_f32")
+        ctx.reg_dims = tuple(reg_dims)
+        ctx.sd_is_log = bool(sd_is_log)
+        ctx.save_for_backward(loc, sd, eps, grad_cols if want_grad else None, scal, scale)
+        return z, scale, scal[0], scal[1]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dz, dscale_up, dkld, dreg):
+        loc, sd, eps, grad_cols, scal, scale = ctx.saved_tensors
+        lib = _lib.load()
+        dev = loc.device
+        B, Z = loc.shape
+        need_loc, need_sd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        with torch.cuda.device(dev):
+            dloc = torch.empty((B, Z), dtype=torch.float32, device=dev) if need_loc else None
+            dsd = torch.empty((B, Z), dtype=torch.float32, device=dev) if need_sd else None
+            rc = lib.arvae_head_fused_bwd_f32(
+                _ptr(loc), _ptr(sd), 1 if ctx.sd_is_log else 0, _ptr(eps), _ptr(_f32c(dz)), _ptr(grad_cols),
+                _ptr(_f32c(dreg)), _lib.i32_array(ctx.reg_dims), len(ctx.reg_dims), ctypes.c_void_p(scal.data_ptr() + 8),
+                _ptr(_f32c(dkld)), B, Z, _ptr(dloc), _ptr(dsd), _stream(dev))
+            _lib.check(rc, "arvae_head_fused_bwd_f32")
+        if dscale_up is not None and dsd is not None and ctx.sd_is_log:
+            dsd = dsd + dscale_up * scale  # somebody differentiated through the returned scale as well
+        return (dloc, dsd) + (None,) * 9
+
+
+def _fused_head_ok(B: int, R: int, algo: int) -> bool:
+    return 1 <= B <= FUSED_HEAD_MAX_BATCH and R >= 1 and algo == ALGO_AUTO
+
+
 def latent_head(loc: torch.Tensor, scale: torch.Tensor, eps: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """``z_tilde`` and the batch-mean KL divergence to the unit prior, fused; differentiable
     w.r.t. ``loc`` and ``scale`` (imagevae/mnist_vae.py:79, utils/trainer.py:364-365)."""
@@ -441,14 +518,39 @@ def reparam_kld_reg(loc: torch.Tensor, scale: torch.Tensor, eps: torch.Tensor, l
     * ``reg_loss = sum_dim gamma * reg_loss_sign(z_tilde[:, dim], labels[:, dim], factor)``
       (trainer.py:369-403 through the trainers' loop)
 
-    One autograd node; its backward is a single pass over [B, Z] that folds the decoder's
-    ``dz``, the regularization gradient and the KLD gradient into ``dloc`` and ``dscale``.
+    One autograd node.  Up to B = 8192 (the sizes the reference trains at) the forward is ONE kernel launch
+    (csrc/head_fused.cu) and the backward another; larger batches run the head kernel and the attribute-sorted
+    pair path.  The backward is a single pass over [B, Z] that folds the decoder's ``dz``, the regularization
+    gradient and the KLD gradient into ``dloc`` and ``dscale``.
     """
     loc, scale, eps = _check_head_inputs(loc, scale, eps)
     dims = _normalize_dims(reg_dims, loc.shape[1])
     lab, lcols = _prepare_labels(labels, dims if label_cols is None else label_cols, loc.shape[0], loc.device)
+    if _fused_head_ok(loc.shape[0], len(dims), int(algo)):
+        z, _, kld_loss, reg_loss = _HeadFusedFn.apply(loc, scale, eps, lab, dims, lcols, _scalar(beta), _scalar(capacity),
+                                                      _scalar(gamma), _scalar(factor), False)
+        return z, kld_loss, reg_loss
     return _HeadRegFn.apply(loc, scale, eps, lab, dims, lcols, _scalar(beta), _scalar(capacity), _scalar(gamma),
                             _scalar(factor), int(algo))
+
+
+def latent_loss_head(loc: torch.Tensor, log_std: torch.Tensor, eps: torch.Tensor, labels: torch.Tensor,
+                     reg_dims: Sequence[int], beta, capacity, gamma, factor=1.0,
+                     label_cols: Optional[Sequence[int]] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The encoder head's ``exp`` included: from ``(z_mean, z_log_std)`` as the encoders produce them
+    (imagevae/mnist_vae.py:63-65, measurevae/encoder.py:120-123) returns ``(z_tilde, scale, kld_loss, reg_loss)`` with
+    ``scale = exp(log_std)`` (what ``Normal(loc, scale)`` is built from) and the other three as in
+    :func:`reparam_kld_reg`.  One launch forward, one backward (gradients w.r.t. ``loc`` and ``log_std``); B <= 8192."""
+    loc, log_std, eps = _check_head_inputs(loc, log_std, eps)
+    dims = _normalize_dims(reg_dims, loc.shape[1])
+    lab, lcols = _prepare_labels(labels, dims if label_cols is None else label_cols, loc.shape[0], loc.device)
+    if not _fused_head_ok(loc.shape[0], len(dims), ALGO_AUTO):
+        scale = torch.exp(log_std)
+        z, kld_loss, reg_loss = reparam_kld_reg(loc, scale, eps, lab, dims, beta, capacity, gamma, factor, lcols)
+        return z, scale, kld_loss, reg_loss
+    return _HeadFusedFn.apply(loc, log_std, eps, lab, dims, lcols, _scalar(beta), _scalar(capacity), _scalar(gamma),
+                              _scalar(factor), True)
 
 
 def reparametrize(z_dist: torch.distributions.Normal):

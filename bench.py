@@ -15,6 +15,9 @@ per-rank sort, sorted runs stored into every peer, merge, 1/N of the single-GPU 
 loss partials pulled from peers.  No NCCL call inside a step (--transport nccl selects the all-gather / all-reduce
 form instead).
 
+`value` is computed from the MEDIAN of the K per-step device times (each step has its own CUDA event pair; max over
+ranks of the per-rank medians); `ms_per_step_mean` is the mean of the same K intervals.
+
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
@@ -39,6 +42,12 @@ MUFU_LANES_PER_CLK_SM = 16.0     # sm_100 MUFU issue rate; confirmed by bench_to
 # MUFU per evaluated pair: 2 (EX2 + RCP on the latent difference, SURVEY App. B's cheapest admissible
 # dense form) on the dense path; 1 (RCP only, E_j/(E_i+E_j) with E = 2^u precomputed per element) where
 # the attribute-sorted path's range guard holds.  Measured per run via arvae_b200.mufu_per_pair().
+# Of every 16 pairs of the one-MUFU constant-sign loop, ARVAE_NR_PAIRS (reg_sorted.cu) take their reciprocal from a
+# Newton iteration on the FMA pipe instead of MUFU.RCP; SASS of that loop (cuobjdump): 204 instructions per 32 pairs,
+# 26 of them MUFU.  Used for the roof of the ACTUAL instruction mix.
+NR_PAIRS_OF_16 = 3
+CONST_LOOP_INSTR_PER_PAIR = 204.0 / 32.0
+ISSUE_LANES_PER_CLK_SM = 128.0   # 4 schedulers x 32 lanes
 ALGO_BYTES_PER_ROWCOL = 4        # float32 per latent / label / gradient element
 # (B, R, n_gpus, algo) -> dram__bytes_read.sum + dram__bytes_write.sum of one pair-kernel launch (ncu, profiles/)
 NCU_DRAM_BYTES_PER_LAUNCH = {(65536, 6, 1, 0): 5261056 + 0}
@@ -151,6 +160,58 @@ def cpu_reference_sample(case, target_seconds: float, steps: int = 1, warmup: in
     }
 
 
+def _import_reference_trainer():
+    """The reference's own Trainer (utils/trainer.py) when its tree is on this box (the dev container), else None."""
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        return None
+    import types
+    for name in ("tensorboardX", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["tensorboardX"].SummaryWriter = object
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        from utils.trainer import Trainer
+        return Trainer
+    except Exception:
+        return None
+
+
+def cpu_full_dense_chain(B: int, steps: int, budget_s: float):
+    """The COMPLETE dense op chain (all B x B temporaries, forward + autograd backward, the trainers' per-dim loop) at
+    a batch size that fits in host memory -- the unmodified reference when /root/reference exists, else the port."""
+    from arvae_b200 import synth
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    case = synth.make_case(WORKLOAD, B)
+    Trainer = _import_reference_trainer()
+    fn = Trainer.compute_reg_loss if Trainer is not None else torch_port.compute_reg_loss
+    kind = "reference" if Trainer is not None else "port (the reference tree is not on this box)"
+    z0, labels = case["z"], case["labels"]
+
+    def run():
+        z = z0.clone().requires_grad_(True)
+        t = time.perf_counter()
+        loss = 0.0
+        for dim in case["reg_dims"]:  # imagevae/image_vae_trainer.py:171-180
+            loss = loss + fn(z, labels[:, dim], dim, gamma=case["gamma"], factor=case["delta"])
+        loss.backward()
+        return time.perf_counter() - t
+
+    t_first = run()
+    n = int(max(1, min(steps, (budget_s - t_first) // max(t_first, 1e-3))))
+    times = [run() for _ in range(n)]
+    dt = statistics.median(times)
+    R = len(case["reg_dims"])
+    return {"B": B, "Z": case["Z"], "R": R, "value": float(B) * B * R / dt / 1e9, "unit": "Gpairs/s",
+            "ms_per_step": dt * 1e3, "steps": n, "cores": threads, "kind": kind, "same_config_except_B": True,
+            "note": f"complete dense chain at the largest batch that fits in host memory; {WORKLOAD} itself (B=65536) "
+                    "needs 16 GiB per B x B temporary and cannot run"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -158,16 +219,22 @@ def run_reference_arm(args):
     from arvae_b200 import synth
     case = synth.make_case(WORKLOAD, args.batch or None)
     B, R = case["B"], len(case["reg_dims"])
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    value, info = cpu_reference_sample(case, min(20.0, budget), steps=args.steps, warmup=args.warmup)
+    n_runs = max(1, args.steps + args.warmup)
+    value, info = cpu_reference_sample(case, min(20.0, 110.0 / n_runs), steps=args.steps, warmup=args.warmup)
+    try:
+        dense = cpu_full_dense_chain(8192, steps=3, budget_s=60.0)
+    except Exception as e:  # pragma: no cover
+        dense = {"B": 8192, "value": None, "note": f"failed: {e}"}
+    kind = info["kind"] if os.path.isdir("/root/reference") else "port (the reference tree is not on this box)"
     line = {
         "impl": "reference", "metric": "reg_loss_fwd_bwd_throughput", "value": value, "unit": "Gpairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "B": B, "Z": case["Z"], "R": R, "gamma": case["gamma"],
                    "delta": case["delta"], "pairs_per_step": float(B) * B * R},
-        "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": info["cores"], "kind": info["kind"],
+        "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": info["cores"], "kind": kind,
                          "sample": info["sample"]},
+        "full_dense_chain": dense,
         "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -179,6 +246,96 @@ def run_reference_arm(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 _REAL_STDOUT = None
+
+
+def parity_block(case, grad_local, r0, n_local, loss_val, dev, world, dist):
+    """Gradient rows of 16 samples of this rank vs float64; max over ranks.  Also: is the loss bit-identical on all ranks."""
+    dims = list(case["reg_dims"])
+    B = case["B"]
+    z = case["z"].to(dev, torch.float64)
+    a = case["labels"].to(dev)
+    rows = torch.linspace(0, n_local - 1, 16).long().unique().to(dev)
+    gi = rows + r0
+    worst = 0.0
+    for d in dims:
+        x, ad = z[:, d], a[:, d]
+        t = torch.tanh(case["delta"] * (x[gi, None] - x[None, :]))
+        s = torch.sign(ad[gi, None] - ad[None, :]).double()
+        g_ref = (2.0 * case["gamma"] * case["delta"] / (float(B) * B)) * (torch.sign(t - s) * (1.0 - t * t)).sum(1)
+        # the gate of tests/util.py: error against the column's magnitude (taken over the sampled rows)
+        err = (grad_local[rows, d].double() - g_ref).abs().max() / g_ref.abs().max().clamp_min(1e-300)
+        worst = max(worst, float(err))
+    stats = torch.tensor([worst, loss_val, -loss_val], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    return {"grad_rows_max_rel_err_vs_f64": float(stats[0]), "rows_checked_per_rank": int(rows.numel()),
+            "loss_bit_identical_on_all_ranks": bool(float(stats[1]) == -float(stats[2])), "gate": 1e-5,
+            "ok": bool(float(stats[0]) <= 1e-5 and float(stats[1]) == -float(stats[2]))}
+
+
+def small_batch_extra(dev):
+    """the whole latent-loss head (reparametrize + KLD + reg loss, forward AND backward: one
+    kernel launch each) on the reference's real configurations.
+    device_us: device time per forward+backward, from 20 back-to-back replays of ONE CUDA graph holding both launches
+               (and autograd's gradient accumulation), so that no host latency sits between the kernels;
+    eager_us:  the same step issued eagerly through the Python API (autograd dispatch included), one step per event
+               pair -- host-bound at these sizes."""
+    import arvae_b200
+    from arvae_b200 import graphs, synth
+    out = {}
+    for name, beta, cap in (("c1_mnist_b64", 4.0, 0.0), ("c2_dsprites_b4096", 4.0, 0.0), ("c3_measure_b2048", 0.001, 0.0)):
+        c = synth.make_case(name)
+        B, Z, dims = c["B"], c["Z"], tuple(c["reg_dims"])
+        loc0, log_std0, eps0 = synth.make_latent_head(B, Z, 77)
+        loc = loc0.to(dev).requires_grad_(True)
+        scale = torch.exp(log_std0).to(dev).requires_grad_(True)
+        eps, lab = eps0.to(dev), c["labels"].to(dev)
+
+        def step():
+            z, kld, reg = arvae_b200.reparam_kld_reg(loc, scale, eps, lab, dims, beta, cap, c["gamma"], c["delta"])
+            (kld + reg).backward()
+            return kld, reg
+
+        res = {"B": B, "Z": Z, "R": len(dims), "pairs": float(B) * B * len(dims), "launches_fwd": 1, "launches_bwd": 1}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                loc.grad = scale.grad = None
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        ts = []
+        for _ in range(30):
+            loc.grad = scale.grad = None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        res["eager_us"] = statistics.median(ts)
+        try:
+            graph = torch.cuda.CUDAGraph()
+            loc.grad = scale.grad = None
+            with graphs.quiet_gc(), torch.cuda.graph(graph):
+                kld, reg = step()
+            reps = 20
+            ts = []
+            for _ in range(12):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    graph.replay()
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3 / reps)
+            res["device_us"] = statistics.median(ts[2:])
+            res["gpairs_per_s_device"] = res["pairs"] / (res["device_us"] * 1e-6) / 1e9
+            res["graph_losses"] = [float(kld.detach()), float(reg.detach())]
+        except Exception as e:  # pragma: no cover
+            res["graph_error"] = str(e)
+        out[name] = res
+    return out
 
 
 def _claim_stdout():
@@ -206,6 +363,7 @@ def main():
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 dense, 2 sorted")
     ap.add_argument("--batch", type=int, default=0, help="override B (parity/scaling sweeps; 0 = config C4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small-batch", action="store_true", help="skip extra.small_batch (the C1-C3 head timings)")
     ap.add_argument("--transport", default="nvlink", choices=["nvlink", "nccl"],
                     help="N>1: nvlink = peer-memory exchange inside the kernels (ShardComm); nccl = all-gather + all-reduce")
     ap.add_argument("--graph", type=int, default=0,
@@ -318,7 +476,8 @@ def main():
     def timed(fn, steps, do_flush):
         """K steps bracketed by barrier + synchronize on both sides.  Every step is timed on the device with
         its own CUDA event pair; the L2 flush (a 256 MiB memset, ~0.07 ms) runs BETWEEN the steps, outside the
-        per-step intervals.  Returns (sum of the K step times in ms, max over ranks; bracket time incl. flushes)."""
+        per-step intervals.  Returns (sum of the K step times in ms, ..., bracket time incl. flushes, median step
+        time), each the max over ranks."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         br0 = torch.cuda.Event(enable_timing=True)
         br1 = torch.cuda.Event(enable_timing=True)
@@ -335,13 +494,15 @@ def main():
         br1.record()
         barrier()
         t1 = time.time()
-        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
+        ms = sum(per_step)
+        ms_med = statistics.median(per_step)
         ms_bracket = br0.elapsed_time(br1)
         if world > 1:
-            t = torch.tensor([ms, ms_bracket], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms, ms_bracket, ms_med], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, ms_bracket = float(t[0].item()), float(t[1].item())
-        return ms, out, t0, t1, ms_bracket
+            ms, ms_bracket, ms_med = float(t[0].item()), float(t[1].item()), float(t[2].item())
+        return ms, out, t0, t1, ms_bracket, ms_med
 
     # ---- warm-up ------------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -358,22 +519,27 @@ def main():
         time.sleep(0.3)
     lib.arvae_launch_count(1)
     lib.arvae_profile_enable(1)
-    ms_total, out, t0, t1, ms_bracket = timed(step_device, args.steps, True)
+    ms_total, out, t0, t1, ms_bracket, ms_median = timed(step_device, args.steps, True)
     ksum, kn = ctypes.c_float(), ctypes.c_int()
     lib.arvae_profile_pair_kernel_ms(ctypes.byref(ksum), ctypes.byref(kn))
     lib.arvae_profile_enable(0)
     launches = int(lib.arvae_launch_count(1))
     loss_val = float(out[0].item())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    ms_step = ms_total / args.steps
+    ms_step_mean = ms_total / args.steps
+    ms_step = ms_median
     value = pairs / (ms_step * 1e-3) / 1e9
+    grad_dev = out[1]
 
     # ---- end-to-end timing (host buffers in, host results out) -----------------------------------
-    ms_e2e_total, loss_e2e, _, _, _ = timed(step_e2e, args.steps, True)
-    ms_e2e = ms_e2e_total / args.steps
+    ms_e2e_total, loss_e2e, _, _, _, ms_e2e = timed(step_e2e, args.steps, True)
     e2e_value = pairs / (ms_e2e * 1e-3) / 1e9
     h2d = z_host.numel() * 4 + lab_host.numel() * 4
     d2h = grad_host.numel() * 4 + 4
+
+    # ---- parity of THIS run's results: sampled rows of every rank against a float64 evaluation of the reference
+    # formula (utils/trainer.py:390-401 and its autograd backward) done with torch on the device
+    parity = parity_block(case, grad_dev, r0, n_local, loss_val, dev, world, dist if world > 1 else None)
 
     if comm is not None:
         comm.close()
@@ -388,7 +554,12 @@ def main():
     f_ghz = float(peaks.get("sm_max_mhz", 1965.0)) / 1e3
     per_dim = arvae_b200.mufu_per_pair(case["z"].to(dev), case["labels"].to(dev), dims, gamma, delta, algo=args.algo)
     MUFU_PER_PAIR = sum(per_dim) / len(per_dim)
-    mufu_peak = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / MUFU_PER_PAIR  # Gpairs/s per GPU
+    mufu_peak = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / MUFU_PER_PAIR  # Gpairs/s per GPU, one MUFU per inlier pair
+    # the kernel's ACTUAL mix: NR_PAIRS_OF_16 of every 16 inlier pairs take the reciprocal on the FMA pipe
+    mufu_mix = MUFU_PER_PAIR - (NR_PAIRS_OF_16 / 16.0) * (2.0 - MUFU_PER_PAIR)  # outlier pairs keep both MUFU
+    mufu_peak_mix = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / mufu_mix
+    issue_peak_mix = ISSUE_LANES_PER_CLK_SM * sm_count * f_ghz / CONST_LOOP_INSTR_PER_PAIR
+    peak_mix = min(mufu_peak_mix, issue_peak_mix)
     mufu_peak_2 = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / 2.0
     k_ms = (ksum.value / kn.value) if kn.value else ms_step
     pairs_per_launch = pairs / world  # this rank's rows x all columns x R
@@ -398,16 +569,22 @@ def main():
     # under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum); only known for the configuration profiled
     traffic = NCU_DRAM_BYTES_PER_LAUNCH.get((B, R, world, int(args.algo)))
     roofline = {
-        "bound": "mufu", "achieved": achieved, "peak": mufu_peak, "unit": "Gpairs/s", "frac": achieved / mufu_peak,
+        "bound": "mufu", "achieved": achieved, "peak": peak_mix, "unit": "Gpairs/s", "frac": achieved / peak_mix,
         "traffic": traffic,
+        "peak_of_actual_mix": {"mufu_per_pair": mufu_mix, "mufu_roof": mufu_peak_mix, "instr_per_pair": CONST_LOOP_INSTR_PER_PAIR,
+                               "issue_roof": issue_peak_mix,
+                               "note": f"{NR_PAIRS_OF_16} of 16 reciprocals per inlier pair group run as Newton iterations on the "
+                                       "FMA pipe (reg_sorted.cu ARVAE_NR_PAIRS); SASS of the constant-sign loop: 204 instructions "
+                                       "per 32 pairs, 26 MUFU; `peak` = the lower of the two roofs of that mix"},
+        "frac_of_1mufu_roof": achieved / mufu_peak, "peak_1mufu": mufu_peak,
         "traffic_source": "profiles/r1_final_ncu_full_summary.csv (ncu --set full, reg_tiles_kernel<true>)" if traffic else None,
         "peak_source": f"{MUFU_LANES_PER_CLK_SM:.0f} MUFU lanes/clk/SM x {sm_count} SMs x {f_ghz:.3f} GHz (sm_max_mhz, "
-                       f"MEASURED_PEAKS.json {peaks_src}) / {MUFU_PER_PAIR:.2f} MUFU per evaluated pair (this run's "
-                       "algorithm; every one of the B^2 R ordered pairs is evaluated); "
+                       f"MEASURED_PEAKS.json {peaks_src}) / {mufu_mix:.4f} MUFU per evaluated pair (this run's "
+                       "algorithm and instruction mix; every one of the B^2 R ordered pairs is evaluated); "
                        "lane rate confirmed by bench_tools/pipe_rates.cu (profiles/)",
         "frac_of_2mufu_dense_roof": achieved / mufu_peak_2, "peak_2mufu_dense": mufu_peak_2,
         "mufu_per_pair_by_dim": list(per_dim),
-        "kernel": "reg pair kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
+        "kernel": "reg pair kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step_mean,
         "evaluated_pairs_per_launch": pairs_per_launch, "mufu_per_pair": MUFU_PER_PAIR,
         "algorithmic_bytes_per_launch": algo_bytes,
         "hbm": {"achieved_gbs": algo_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
@@ -426,9 +603,18 @@ def main():
             cpu_baseline = {"value": None, "unit": "Gpairs/s", "cores": os.cpu_count(), "kind": "port",
                             "sample": f"failed: {e}"}
 
+    extra = {}
+    if world == 1 and not args.no_small_batch:
+        try:
+            extra["small_batch"] = small_batch_extra(dev)
+            extra["small_batch"]["clocks"] = clocks
+        except Exception as e:  # pragma: no cover
+            extra["small_batch"] = {"error": str(e)}
+
     line = {
         "metric": "reg_loss_fwd_bwd_throughput", "value": value, "unit": "Gpairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_mean": ms_step_mean,
+        "fixed_ms": ms_step - k_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "B": B, "Z": Z, "R": R, "gamma": gamma, "delta": delta,
                    "pairs_per_step": pairs, "parallelism": f"row-block x{world}" if world > 1 else "single GPU",
@@ -440,7 +626,7 @@ def main():
         "clocks": clocks, "e2e": {"value": e2e_value, "unit": "Gpairs/s", "ms_per_step": ms_e2e,
                                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "loss": loss_val, "loss_e2e": loss_e2e,
+        "parity": parity, "extra": extra, "loss": loss_val, "loss_e2e": loss_e2e,
     }
     emit(line)
     if world > 1:

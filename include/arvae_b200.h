@@ -157,6 +157,38 @@ ARVAE_API int arvae_latent_head_bwd_f32(const float *loc_dev, const float *scale
                               void *stream);
 
 /*
+ * The whole latent-loss head in ONE launch (csrc/head_fused.cu), for 1 <= B <= 8192 -- the sizes the reference
+ * trains at (B = 128 / 256: train_image_vae.py:16, train_measure_vae.py:35):
+ *   scale = sd, or exp(sd) when sd_is_log_std (imagevae/mnist_vae.py:63-65, measurevae/encoder.py:120-123)
+ *   z        = loc + eps*scale                                    (mnist_vae.py:79, measure_vae.py:116)
+ *   kld_mean, kld_loss = beta*|kld_mean - capacity|, kcoef        (utils/trainer.py:354-367; as latent_head_fwd)
+ *   reg_loss = sum_r gamma * mean_ij |tanh(factor (z_i - z_j)) - sign(a_i - a_j)| over z[:, reg_dims[r]],
+ *              labels[:, label_cols[r]]                          (utils/trainer.py:369-403 via the trainers' loop)
+ *   grad_cols[b, r] = d reg_loss / d z[b, reg_dims[r]]           (NULL: no gradient wanted)
+ * loc/sd/eps/z_out/scale_out [B,Z] float contiguous; labels with element strides; scale_out / kld_* / kcoef may
+ * be NULL.  workspace_dev: arvae_head_fused_workspace_bytes(B, R) bytes that the CALLER ZEROES ONCE (e.g. at
+ * allocation); every launch leaves it zeroed again, so the same buffer serves every later call on the same stream
+ * (no memset per call, CUDA-graph capturable).  Returns ARVAE_E_BADARG for B > 8192: use arvae_latent_head_fwd_f32 +
+ * arvae_reg_loss_fwdbwd_f32 there.
+ *
+ * Backward in one launch (arvae_latent_head_bwd_f32's pass with kscale = 1): dloc, and dsd = d/d(scale), or
+ * d/d(log_std) = d/d(scale) * scale when sd_is_log_std.
+ */
+ARVAE_API size_t arvae_head_fused_workspace_bytes(int64_t B, int32_t R);
+ARVAE_API int arvae_head_fused_fwd_f32(const float *loc_dev, const float *sd_dev, int32_t sd_is_log_std,
+                             const float *eps_dev, int64_t B, int64_t Z, const float *labels_dev,
+                             int64_t lab_row_stride, int64_t lab_col_stride, const int32_t *reg_dims_host,
+                             const int32_t *label_cols_host, int32_t R, float beta, float capacity, float gamma,
+                             float factor, float *z_out_dev, float *scale_out_dev, float *kld_mean_out_dev,
+                             float *kld_loss_out_dev, float *kcoef_out_dev, float *reg_loss_out_dev,
+                             float *grad_cols_out_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+ARVAE_API int arvae_head_fused_bwd_f32(const float *loc_dev, const float *sd_dev, int32_t sd_is_log_std,
+                             const float *eps_dev, const float *dz_up_dev, const float *grad_cols_dev,
+                             const float *greg_dev, const int32_t *reg_dims_host, int32_t R,
+                             const float *kcoef_dev, const float *gkld_dev, int64_t B, int64_t Z,
+                             float *dloc_dev, float *dsd_dev, void *stream);
+
+/*
  * Host-buffer form of the compute_reg_loss loop (the end-to-end call): copies z and labels to the
  * device, runs the fused forward+backward over all rows, copies the loss and dLoss/dz back.
  *   z_host [B,Z] float row-major, labels_host [B,A] float row-major

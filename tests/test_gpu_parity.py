@@ -348,6 +348,17 @@ def test_c4_full_size_row_samples_and_properties(ab, oracle_mod, algo):
     assert np.array_equal(g_mono.cpu().numpy(), grad_cols)
 
 
+def test_bool_and_uint8_labels_are_refused(ab):
+    """The reference raises on bool labels (`a - a.T`, utils/trainer.py:395) and, for uint8, takes the sign of a
+    WRAPPED difference; neither is computed silently here."""
+    z = torch.randn(8, 2, device="cuda")
+    with pytest.raises(RuntimeError, match="bool tensors is not supported"):
+        ab.compute_reg_loss(z, torch.zeros(8, dtype=torch.bool, device="cuda"), 0, 1.0)
+    with pytest.raises(RuntimeError, match="uint8"):
+        ab.compute_reg_loss(z, torch.zeros(8, dtype=torch.uint8, device="cuda"), 0, 1.0)
+    ab.compute_reg_loss(z, torch.zeros(8, dtype=torch.int8, device="cuda"), 0, 1.0)  # signed narrow ints are exact in f32
+
+
 # ------------------------------------------------------------------------------------------------
 # latent head: reparametrize + KLD (+ reg) fused
 # ------------------------------------------------------------------------------------------------
@@ -367,6 +378,53 @@ def test_fused_head_matches_reference(ab):
     assert_grad_close(loc.grad.cpu().numpy(), g["grad_loc"])
     assert_grad_close(scale.grad.cpu().numpy(), g["grad_scale"])
     assert_grad_close((scale.grad * scale.detach()).cpu().numpy(), g["grad_log_std"])  # exp backward
+
+
+def test_one_launch_head_from_log_std_matches_reference(ab):
+    """exp(log_std) + rsample + KLD + reg in ONE launch, ONE more for the backward (csrc/head_fused.cu), against the
+    unmodified reference's outputs (goldens).  CUDA expf and the CPU's exp differ in the last ulp, so z_tilde is
+    compared to 2 ulp of its terms here (loc + eps * scale cancels near zero); the bit-identical check is
+    test_fused_head_matches_reference (scale given)."""
+    from arvae_b200 import _lib
+    lib = _lib.load()
+    g = golden("head_c3_measure_b2048")
+    dims = tuple(int(d) for d in g["reg_dims"])
+    for rep in range(3):  # the same zero-once workspace serves every call
+        loc = dev(g["loc"]).requires_grad_(True)
+        log_std = dev(g["log_std"]).requires_grad_(True)
+        lib.arvae_launch_count(1)
+        z, scale, kld, reg = ab.latent_loss_head(loc, log_std, dev(g["eps"]), dev(g["labels"]), dims, float(g["beta"]),
+                                                 float(g["capacity"]), float(g["gamma"]), float(g["delta"]))
+        assert lib.arvae_launch_count(1) == 1
+        np.testing.assert_allclose(z.detach().cpu().numpy(), g["z_tilde"], rtol=3e-7, atol=1e-6)
+        np.testing.assert_allclose(scale.detach().cpu().numpy(), np.exp(g["log_std"]), rtol=3e-7)
+        assert_loss_close(kld.item(), g["kld_loss"])
+        assert_loss_close(reg.item(), g["reg_loss"])
+        (kld + reg).backward()
+        assert lib.arvae_launch_count(1) == 1
+        assert_grad_close(loc.grad.cpu().numpy(), g["grad_loc"])
+        assert_grad_close(log_std.grad.cpu().numpy(), g["grad_log_std"])
+
+
+@pytest.mark.parametrize("name", ["reg_c1_mnist_b64", "reg_c2_dsprites_b512", "reg_c2_dsprites_b4096", "edge_rand_b129",
+                                  "edge_nan_inf_labels", "edge_b1", "edge_negative_factor"])
+def test_one_launch_head_reg_part_matches_reg_goldens(ab, name):
+    """The pair sweep inside the one-launch head against the reference's reg-loss goldens: loc = z, eps = 0."""
+    g = golden(name)
+    if "z" in g:   # trainer-loop fixtures: z [B, Z], labels [B, A], reg_dims
+        z0, labels = dev(g["z"]), dev(g["labels"])
+        dims = tuple(int(d) for d in g["reg_dims"])
+        gamma, ref = float(g["gamma"]), g["grad_z"]
+    else:          # reg_loss_sign fixtures: x [B], a [B]
+        z0, labels = dev(g["x"]).reshape(-1, 1), dev(g["a"]).reshape(-1, 1)
+        dims, gamma, ref = (0,), 1.0, g["grad_x"].reshape(-1, 1)
+    loc = z0.clone().requires_grad_(True)
+    z, kld, reg = ab.reparam_kld_reg(loc, torch.ones_like(loc), torch.zeros_like(loc), labels, dims, 0.0, 0.0, gamma,
+                                     float(g["delta"]))
+    assert torch.equal(z.detach(), z0)
+    assert_loss_close(reg.item(), float(g["loss"]))
+    reg.backward()
+    assert_grad_close(loc.grad.cpu().numpy(), ref)
 
 
 def test_fused_head_with_decoder_gradient(ab):
