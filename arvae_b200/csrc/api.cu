@@ -701,8 +701,7 @@ int arvae_shard_reg_loss_host_f32(void *ctx, const float *z_local_host, int64_t 
             return ARVAE_E_BADARG;
         }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t zb = sizeof(float) * (size_t)C->n_cap * Z, lb = sizeof(float) * (size_t)C->n_cap * A,
-                 gb = sizeof(float) * (size_t)C->n_cap * C->R_cap;
+    const size_t zb = sizeof(float) * (size_t)C->n_cap * Z, lb = sizeof(float) * (size_t)C->n_cap * A;
     if (C->h_z_bytes < zb) {
         cudaFree(C->h_z); cudaFree(C->h_gz);
         C->h_z = C->h_gz = nullptr; C->h_z_bytes = 0;
@@ -716,33 +715,44 @@ int arvae_shard_reg_loss_host_f32(void *ctx, const float *z_local_host, int64_t 
         ARVAE_CUDA_TRY(cudaMalloc(&C->h_lab, lb));
         C->h_lab_bytes = lb;
     }
-    if (C->h_gc_bytes < gb) {
-        cudaFree(C->h_gc);
-        C->h_gc = nullptr; C->h_gc_bytes = 0;
-        ARVAE_CUDA_TRY(cudaMalloc(&C->h_gc, gb));
-        C->h_gc_bytes = gb;
-    }
-    if (!C->h_loss) ARVAE_CUDA_TRY(cudaMalloc(&C->h_loss, sizeof(double)));
+    if (!C->h_loss_host) ARVAE_CUDA_TRY(cudaHostAlloc(&C->h_loss_host, sizeof(double), cudaHostAllocMapped));
+    if (!C->h_aux) ARVAE_CUDA_TRY(cudaStreamCreateWithFlags(&C->h_aux, cudaStreamNonBlocking));
+    if (!C->h_ev) ARVAE_CUDA_TRY(cudaEventCreateWithFlags(&C->h_ev, cudaEventDisableTiming));
     if (n > 0) {
+        // the two inputs travel side by side: labels on a second stream, joined before the sort kernel
+        ARVAE_CUDA_TRY(cudaMemcpyAsync(C->h_lab, labels_local_host, sizeof(float) * (size_t)n * A, cudaMemcpyHostToDevice, C->h_aux));
+        ARVAE_CUDA_TRY(cudaEventRecord(C->h_ev, C->h_aux));
         ARVAE_CUDA_TRY(cudaMemcpyAsync(C->h_z, z_local_host, sizeof(float) * (size_t)n * Z, cudaMemcpyHostToDevice, st));
-        ARVAE_CUDA_TRY(cudaMemcpyAsync(C->h_lab, labels_local_host, sizeof(float) * (size_t)n * A, cudaMemcpyHostToDevice, st));
+        ARVAE_CUDA_TRY(cudaStreamWaitEvent(st, C->h_ev, 0));
     }
+    // Where the finalize kernel writes the gradient: straight into the caller's buffer when that is pinned host memory
+    // (mapped into the device under unified addressing: no device-to-host copy, no extra launch), else a device buffer.
+    float *gz_dev = nullptr;
+    bool gz_direct = false;
+    if (grad_z_out_host && n > 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, grad_z_out_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+            gz_dev = reinterpret_cast<float *>(pa.devicePointer);
+            gz_direct = true;
+        } else {
+            (void)cudaGetLastError();
+            gz_dev = C->h_gz;
+        }
+    }
+    double *loss_dev = nullptr;
+    ARVAE_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&loss_dev), C->h_loss_host, 0));
     S.z = C->h_z; S.zrs = Z; S.zcs = 1;
     S.lab = C->h_lab; S.lrs = A; S.lcs = 1;
     S.gamma = gamma; S.factor = factor;
-    S.loss_out = C->h_loss; S.loss_f32_out = nullptr; S.grad_cols_out = grad_z_out_host ? C->h_gc : nullptr;
+    S.loss_out = loss_dev; S.loss_f32_out = nullptr; S.grad_cols_out = nullptr;
+    S.grad_z_out = gz_dev; S.grad_z_cols = Z;
     S.phases = 0;
     rc = run_shard_step(*C, S, st);
     if (rc) return rc;
-    if (grad_z_out_host && n > 0) {
-        rc = run_scatter_bwd(C->h_gc, nullptr, S.dims, R, n, Z, C->h_gz, Z, st);
-        if (rc) return rc;
+    if (gz_dev && !gz_direct)
         ARVAE_CUDA_TRY(cudaMemcpyAsync(grad_z_out_host, C->h_gz, sizeof(float) * (size_t)n * Z, cudaMemcpyDeviceToHost, st));
-    }
-    double loss = 0.0;
-    ARVAE_CUDA_TRY(cudaMemcpyAsync(&loss, C->h_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     ARVAE_CUDA_TRY(cudaStreamSynchronize(st));
-    *loss_out_host = (float)loss;
+    *loss_out_host = (float)*C->h_loss_host;
     return 0;
 }
 
@@ -776,7 +786,10 @@ int arvae_shard_destroy(void *ctx) {
     for (int h = 0; h < C->G; ++h)
         if (C->opened[h]) cudaIpcCloseMemHandle(C->peer[h]);
     cudaFree(C->comm); cudaFree(C->ws);
-    cudaFree(C->h_z); cudaFree(C->h_gz); cudaFree(C->h_lab); cudaFree(C->h_gc); cudaFree(C->h_loss);
+    cudaFree(C->h_z); cudaFree(C->h_gz); cudaFree(C->h_lab);
+    if (C->h_loss_host) cudaFreeHost(C->h_loss_host);
+    if (C->h_aux) cudaStreamDestroy(C->h_aux);
+    if (C->h_ev) cudaEventDestroy(C->h_ev);
     (void)cudaGetLastError();
     delete C;
     return 0;

@@ -45,6 +45,29 @@ struct NvtxRange {
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
+// ---- programmatic dependent launch (sm_90+) ----------------------------------------------------
+// A kernel launched with launch_kernel(..., pdl = true) may start while the previous kernel of the stream is still
+// running: pdl_wait() blocks until that kernel has completed and its writes are visible (a no-op in a normally
+// launched kernel); pdl_trigger() lets the NEXT kernel of the stream start early once every CTA has issued it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                        Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device math ------------------------------------------------------------------------------
 // Single-instruction MUFU ops. The .ftz forms compile to one MUFU each (no range fix-up code);
 // flushing only affects |2^d| < 2^-126, where tanh is already saturated to +-1 in float.

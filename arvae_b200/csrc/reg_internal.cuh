@@ -198,9 +198,11 @@ struct ShardCtx {
     int runs_cap = 0;           // run slots per buffer
     char *ws = nullptr;         // private workspace (sorted columns, plan, ...)
     size_t ws_bytes = 0, off_mypos = 0;
-    float *h_z = nullptr, *h_lab = nullptr, *h_gz = nullptr, *h_gc = nullptr;  // device staging of the host-buffer entry
-    double *h_loss = nullptr;
-    size_t h_z_bytes = 0, h_lab_bytes = 0, h_gc_bytes = 0;
+    float *h_z = nullptr, *h_lab = nullptr, *h_gz = nullptr;  // device staging of the host-buffer entry
+    double *h_loss_host = nullptr;  // pinned, mapped: the finalize kernel writes the loss straight into host memory
+    size_t h_z_bytes = 0, h_lab_bytes = 0;
+    cudaStream_t h_aux = nullptr;   // second copy stream of the host-buffer entry (labels travel beside the latents)
+    cudaEvent_t h_ev = nullptr;
 };
 struct ShardStep {
     const float *z; int64_t zrs, zcs;       // this rank's latents [n_local, *]
@@ -210,6 +212,8 @@ struct ShardStep {
     float gamma, factor;
     double *loss_out; float *loss_f32_out;  // [1] global loss (device)
     float *grad_cols_out;                   // [n_local, R] or null
+    float *grad_z_out = nullptr;            // [n_local, grad_z_cols] dLoss/dz written by the finalize kernel itself (device
+    int64_t grad_z_cols = 0;                // memory, or host memory mapped into the device), or null
     int phases;                             // bit 0: sort + publish, bit 1: rank own runs, bit 2: apply + plan + pair kernel, bit 3: finalize; 0 = all
 };
 size_t shard_comm_bytes(int64_t n_cap, int R_cap, int G, ShardCtx *fill);

@@ -141,6 +141,7 @@ __device__ __forceinline__ uint4 load_run_elem(const RunElem *p, unsigned int ep
             atomicExch(status, 1);
             break;
         }
+        __nanosleep(100);  // the producer may share this SM (overlapped launches): leave it the issue slots
         v = load_run_elem_once<VALIDATE>(p);
     }
     return v;
@@ -226,6 +227,7 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
                   float *__restrict__ Es, int *__restrict__ perm, int *__restrict__ flags, int *__restrict__ mypos,
                   int64_t my_lo, int64_t my_hi, int64_t mypos_stride, int win_cap, PosDest pd, int blk_begin, int dbg) {
     long long tk[6]; tk[0] = clock64();
+    pdl_trigger();  // (sharded step) the apply kernel may start: it waits for every position by itself
     extern __shared__ __align__(16) unsigned long long dyn_smem[];  // [T][kRunPivots] pivot keys, then [win_cap] window keys
     unsigned long long *piv = dyn_smem;
     unsigned long long *win = dyn_smem + (size_t)rs.T * kRunPivots;
@@ -357,6 +359,9 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
         printf("runs_merge T=%d window %d staged %d cycles: load %lld bounds %lld stage %lld rank+write %lld\n", rs.T, total, (int)staged,
                tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], (long long)clock64() - tk[3]);
     if (blockIdx.x == 0 && pd.n_dest == 0) count_inliers<VALIDATE>(rs, r, epoch, flags);
+    // launched overlapped with the sort (sharded step): do not complete before it has, so that "this kernel is
+    // complete" keeps implying "everything before it in the stream is complete" for the kernels that follow
+    pdl_wait();
 }
 
 // A sharded step's second half of the merge: every element of every run of dim r goes to the position its owner
@@ -368,6 +373,7 @@ runs_apply_kernel(RunSet rs, char *__restrict__ pos_base, int64_t Bpad, float ca
     const int64_t B = rs.run_off[rs.T];
     const int64_t base = (int64_t)r * Bpad;
     const int n_blocks = rs.blk_off[rs.T];
+    pdl_trigger();
     if ((int)blockIdx.x >= n_blocks) {  // padding, as in the merge
         const int64_t t = B + (int64_t)(blockIdx.x - n_blocks) * kMergeThreads + tid;
         if (t < Bpad) {
@@ -376,6 +382,7 @@ runs_apply_kernel(RunSet rs, char *__restrict__ pos_base, int64_t Bpad, float ca
             Es[base + t] = 8.5070592e37f;
             perm[base + t] = -1;
         }
+        pdl_wait();
         return;
     }
     const unsigned int epoch = (unsigned int)(*rs.epoch_ctr + 1ull);
@@ -399,11 +406,13 @@ runs_apply_kernel(RunSet rs, char *__restrict__ pos_base, int64_t Bpad, float ca
                 atomicExch(rs.status, 1);
                 break;
             }
+            __nanosleep(100);
             asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(pe.x), "=r"(pe.y) : "l"(pp) : "memory");
         }
         if (pe.y == epoch && (int64_t)pe.x < B) place_run_elem(e, (int64_t)pe.x, base, cabs, Xs, As, Es, perm, flags, r);
     }
     if (blockIdx.x == 0) count_inliers<true>(rs, r, epoch, flags);
+    pdl_wait();  // launched overlapped with the ranking kernel: complete only after it (and, through it, the sort)
 }
 
 // Fills `rs` for runs made of `n_parts` consecutive parts (ranks) of the batch, each cut into runs of kRunCap.
@@ -451,9 +460,9 @@ static int launch_runs_merge(const RunSet &rs, int R, int64_t Bpad, float cabs, 
     if (n_blk == 0) return 0;
     dim3 grid((unsigned)n_blk, (unsigned)R);
     static const int dbg = getenv("ARVAE_DEBUG_PHASES") ? 1 : 0;
-    if (rs.epoch_ctr)
-        runs_merge_kernel<true><<<grid, kMergeThreads, smem, st>>>(rs, Bpad, cabs, Xs, As, Es, perm, flags, mypos, my_lo, my_hi,
-                                                                mypos_stride, win_cap, pd, blk_begin, dbg);
+    if (rs.epoch_ctr)  // sharded step: overlapped with the sort kernel before it (every load validates itself)
+        ARVAE_CUDA_TRY(launch_kernel(runs_merge_kernel<true>, grid, dim3(kMergeThreads), smem, st, true, rs, Bpad, cabs, Xs, As, Es, perm,
+                                     flags, mypos, my_lo, my_hi, mypos_stride, win_cap, pd, blk_begin, dbg));
     else
         runs_merge_kernel<false><<<grid, kMergeThreads, smem, st>>>(rs, Bpad, cabs, Xs, As, Es, perm, flags, mypos, my_lo, my_hi,
                                                                  mypos_stride, win_cap, pd, blk_begin, dbg);
@@ -500,30 +509,47 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh /* shared m
 // ------------------------------------------------------------------------------------------------------------
 // (C) finalize: pull this rank's row sums and every rank's loss partial
 // ------------------------------------------------------------------------------------------------------------
+// Row sum of sample i (local index) of dim r, pulled from the accumulators of the 1-2 ranks that swept its sorted
+// position, as a gradient element (NaN where the reference's float arithmetic gives NaN).
+__device__ __forceinline__ float shard_pull_grad(const TilesArgs &a, const ShardView &v, const int *__restrict__ mypos, int r,
+                                                 int64_t i, double gscale) {
+    const int64_t pos = mypos[(int64_t)r * v.n_cap + i];
+    const int64_t rr = (int64_t)r * a.n_row_tiles + pos / kTileRows;
+    const long long T = a.prefix[a.n_rr];
+    const int h0 = (int)(owner_of_pos(a.prefix[rr], T, a.G) / v.Gc);
+    const int h1 = (int)(owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G) / v.Gc);
+    acc_t g = 0;
+    for (int h = h0; h <= h1; ++h) g += ld_relaxed_sys_s64(shard_acc(v, h) + rr * kTileRows + pos % kTileRows);
+    const bool poisoned = row_is_poisoned(a.flags, r, a.Xs[(int64_t)r * a.Bpad + pos]);
+    return poisoned ? __int_as_float(0x7fc00000) : (float)((double)g * kFixScale * gscale);
+}
+
+// Outputs: grad_cols [n, R] (one thread per element), or -- the host-buffer entry -- grad_z [n, Z] with the scatter
+// into the latent columns done here (one thread per element of grad_z; it may be host memory mapped into the device).
 __global__ void __launch_bounds__(256)
 shard_finalize_kernel(TilesArgs a, const int *__restrict__ mypos, int R, double gscale, double lscale,
                       double pad_per_row, float *__restrict__ grad_cols, double *__restrict__ loss_out,
-                      float *__restrict__ loss_f32_out, int *__restrict__ flags_rw) {
+                      float *__restrict__ loss_f32_out, int *__restrict__ flags_rw, float *__restrict__ grad_z, int64_t Z,
+                      RegDims dims) {
     const ShardView &v = a.shard;
     ShardHeader *hdr = shard_header(v, v.g);
+    pdl_wait();  // launched ahead of the pair kernel's end: sleep until it is complete, then wait for the peers
     const unsigned long long epoch = hdr->epoch + 1;
     shard_wait(v, epoch);
     const int64_t n = v.row_off[v.g + 1] - v.row_off[v.g];
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n * R, dim fastest (coalesced stores)
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool broken = *reinterpret_cast<volatile int *>(&hdr->status) != 0;  // a wait gave up: positions may be garbage
-    if (grad_cols && idx < n * R && broken) grad_cols[idx] = __int_as_float(0x7fc00000);
-    if (grad_cols && idx < n * R && !broken) {
-        const int r = (int)(idx % R);
-        const int64_t i = idx / R;
-        const int64_t pos = mypos[(int64_t)r * v.n_cap + i];
-        const int64_t rr = (int64_t)r * a.n_row_tiles + pos / kTileRows;
-        const long long T = a.prefix[a.n_rr];
-        const int h0 = (int)(owner_of_pos(a.prefix[rr], T, a.G) / v.Gc);
-        const int h1 = (int)(owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G) / v.Gc);
-        acc_t g = 0;
-        for (int h = h0; h <= h1; ++h) g += ld_relaxed_sys_s64(shard_acc(v, h) + rr * kTileRows + pos % kTileRows);
-        const bool poisoned = row_is_poisoned(a.flags, r, a.Xs[(int64_t)r * a.Bpad + pos]);
-        grad_cols[idx] = poisoned ? __int_as_float(0x7fc00000) : (float)((double)g * kFixScale * gscale);
+    if (grad_z) {  // over n * Z, column fastest
+        if (idx < n * Z) {
+            const int zc = (int)(idx % Z);
+            const int64_t i = idx / Z;
+            float g = 0.0f;
+            for (int r = 0; r < R; ++r)
+                if (dims.zcol[r] == zc) g += broken ? __int_as_float(0x7fc00000) : shard_pull_grad(a, v, mypos, r, i, gscale);
+            grad_z[idx] = g;
+        }
+    } else if (grad_cols && idx < n * R) {  // over n * R, dim fastest (coalesced stores)
+        grad_cols[idx] = broken ? __int_as_float(0x7fc00000) : shard_pull_grad(a, v, mypos, (int)(idx % R), idx / R, gscale);
     }
     if (blockIdx.x == 0) {
         __shared__ acc_t shl[2][kMaxShardRanks];
@@ -662,7 +688,7 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
     a.B = B;
     a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
     a.shard = v;
-    const bool want_grad = S.grad_cols_out != nullptr;
+    const bool want_grad = S.grad_cols_out != nullptr || S.grad_z_out != nullptr;
 
     if (phases & 1) {
         KeySpec spec;
@@ -698,16 +724,16 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
         timeline_mark(st, "begin C");
         {   // every element of every run to its position (waits for the peers' elements and positions)
             dim3 grid((unsigned)(rs.blk_off[rs.T] + ceil_div(L.Bpad - B, kMergeThreads)), (unsigned)S.R);
-            runs_apply_kernel<<<grid, kMergeThreads, 0, st>>>(rs, C.comm + C.off_pos, L.Bpad, cabs, const_cast<float *>(a.Xs),
-                                                             const_cast<float *>(a.As), const_cast<float *>(a.Es), perm, flags);
+            ARVAE_CUDA_TRY(launch_kernel(runs_apply_kernel, grid, dim3(kMergeThreads), 0, st, true, rs, C.comm + C.off_pos, L.Bpad, cabs,
+                                         const_cast<float *>(a.Xs), const_cast<float *>(a.As), const_cast<float *>(a.Es), perm, flags));
             ARVAE_LAUNCH_CHECK("runs_apply_kernel");
         }
         timeline_mark(st, "wait+apply");
         // The plan kernel also clears the row accumulators.  That is safe only now: every peer has published this
         // step's runs (the merge saw them), hence finished pulling the previous step's row sums.
         int *combo_cost = reinterpret_cast<int *>(ws + L.off_combo);
-        plan_classes_kernel<<<(unsigned)L.n_rr, 256, 0, st>>>(a, combo_cost, want_grad ? 1 : 0,
-                                                             reinterpret_cast<unsigned int *>(flags + kFlagTicket));
+        ARVAE_CUDA_TRY(launch_kernel(plan_classes_kernel, dim3((unsigned)L.n_rr), dim3(256), 0, st, true, a, combo_cost, want_grad ? 1 : 0,
+                                     reinterpret_cast<unsigned int *>(flags + kFlagTicket)));
         ARVAE_LAUNCH_CHECK("plan_classes_kernel");
         timeline_mark(st, "plan");
         profile_begin(st);
@@ -722,9 +748,10 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
         P.B = B; P.gamma = S.gamma; P.factor = S.factor;
         double lscale, gscale, pad_per_row;
         reg_scales(P, L.Bpad, lscale, gscale, pad_per_row);
-        const int64_t work = n_local * S.R;
-        shard_finalize_kernel<<<(unsigned)(work > 0 ? ceil_div(work, 256) : 1), 256, 0, st>>>(
-            a, mypos, S.R, gscale, lscale, pad_per_row, S.grad_cols_out, S.loss_out, S.loss_f32_out, flags);
+        const int64_t work = S.grad_z_out ? n_local * S.grad_z_cols : n_local * S.R;
+        ARVAE_CUDA_TRY(launch_kernel(shard_finalize_kernel, dim3((unsigned)(work > 0 ? ceil_div(work, 256) : 1)), dim3(256), 0, st, true,
+                                     a, mypos, S.R, gscale, lscale, pad_per_row, S.grad_cols_out, S.loss_out, S.loss_f32_out, flags,
+                                     S.grad_z_out, S.grad_z_cols, S.dims));
         ARVAE_LAUNCH_CHECK("shard_finalize_kernel");
         timeline_mark(st, "wait+finalize");
     }

@@ -415,6 +415,7 @@ plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost, int clear_acc, un
     __shared__ float wmin[kTileThreads / 32], wmax[kTileThreads / 32];
     __shared__ int whas[kTileThreads / 32], win[kTileThreads / 32], wmixed[kTileThreads / 32];
     __shared__ int sred[8];
+    pdl_wait();  // (sharded step: launched ahead of the apply kernel's end) the sorted columns must be complete
     const int64_t rr = blockIdx.x;
     const int r = (int)(rr / a.n_row_tiles), I = (int)(rr % a.n_row_tiles);
     const float *Ar = a.As + (int64_t)r * a.Bpad;

@@ -303,6 +303,7 @@ __device__ __forceinline__ int count_below_pow2(const unsigned long long *__rest
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kCsortThreads, 1)
 cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, const unsigned long long *__restrict__ epoch_ctr, int dbg) {
     long long tk[8]; tk[0] = clock64();
+    pdl_trigger();  // a sharded step's ranking kernel may start now: it waits for every run element by itself
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CsortSmem &S = *reinterpret_cast<CsortSmem *>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();

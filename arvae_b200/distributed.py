@@ -201,19 +201,20 @@ class _ShardedRegLossFn(torch.autograd.Function):
         want_grad = bool(ctx.needs_input_grad[0])
         if comm is not None:
             n_all = [int(z_local.shape[0])] * comm.world
-            loss64, _, grad_cols = comm.h.step(z_local.detach(), labels_local.detach(), reg_dims, label_cols, n_all,
+            _, loss32, grad_cols = comm.h.step(z_local.detach(), labels_local.detach(), reg_dims, label_cols, n_all,
                                                gamma, factor, want_grad)
         else:
             packed_local = pack_columns(z_local, labels_local, reg_dims, label_cols)
             packed, row0 = gather_columns(packed_local, group)
             loss64, grad_cols = _rows_backend(packed, R, gamma, factor, row0, row0 + z_local.shape[0], want_grad, algo)
             dist.all_reduce(loss64, op=dist.ReduceOp.SUM, group=group)
+            loss32 = loss64.to(torch.float32)
         ctx.reg_dims = tuple(reg_dims)
         ctx.shape = tuple(z_local.shape)
         ctx.grad_scale = float(grad_scale)
         if want_grad:
             ctx.save_for_backward(grad_cols)
-        return loss64.to(torch.float32)
+        return loss32  # the same rounding of the float64 total, done by the finalize kernel itself
 
     @staticmethod
     @torch.autograd.function.once_differentiable
