@@ -82,6 +82,31 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// Packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2): two IEEE float operations per issued instruction, each rounded exactly
+// like its scalar form, so packing changes issue slots, not results.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float lo, float hi) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) {
+    f2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+    f2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+    f2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // sign(a_i - a_j) exactly as torch.sign of the float difference: equals (a_i>a_j)-(a_i<a_j) for
 // every pair of floats including NaN, +-inf, +-0 and subnormals. Compiled
 // WITHOUT flush-to-zero so distinct subnormals compare unequal.

@@ -194,11 +194,30 @@ __device__ __forceinline__ float rcp_newton(float x) {
     return fmaf(y, e, y);
 }
 
-#ifndef ARVAE_NR_PAIRS
-#define ARVAE_NR_PAIRS 3  // of every 16 pairs of the 1-MUFU constant-sign loop, how many use rcp_newton.  Measured on the C4
-                          // workload (pair kernel, ms): 0 -> 5.86, 2 -> 5.67, 3 -> 5.60, 4 -> 5.81, 5 -> 6.14, 6 -> 6.36: with 3
-                          // of 16 reciprocals on the FMA pipe the XU pipe (13/16 MUFU per pair) and the issue slots balance.
+// The same on two packed values (FFMA2: one issued instruction per Newton step for two reciprocals).
+__device__ __forceinline__ f2_t rcp_newton2(f2_t x) {
+    float x0, x1;
+    unpack2(x, x0, x1);
+    f2_t y = pack2(__int_as_float(0x7EF311C7 - __float_as_int(x0)), __int_as_float(0x7EF311C7 - __float_as_int(x1)));
+    const f2_t one = pack2(1.0f, 1.0f), nx = pack2(-x0, -x1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const f2_t e = fma2(nx, y, one);
+        y = fma2(y, e, y);
+    }
+    return y;
+}
+
+#ifndef ARVAE_NR_MASK
+#define ARVAE_NR_MASK 0xC0  // which of the 8 (row k, column pair h) slots (bit 2 k + h) of a 4 x 4 pair group of the one-MUFU
+                            // constant-sign loop take their two reciprocals from rcp_newton2 (FMA pipe) instead of two
+                            // MUFU.RCP (XU pipe).  Pair kernel on C4, ms: no slot 5.86 (scalar loop), one slot 5.48, two
+                            // slots (0xC0) 5.15, three 5.51
 #endif
+#ifndef ARVAE_CONST_UNROLL
+#define ARVAE_CONST_UNROLL 2
+#endif
+constexpr int kConstUnroll = ARVAE_CONST_UNROLL;
 
 template <bool MUFU1>
 __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs) {
@@ -206,31 +225,73 @@ __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs)
     return rcp_approx(ex2_approx(d * cabs) + 1.0f);       // 1 / (1 + 2^(|c| (xs_i - xs_j)))
 }
 
+// Constant-sign tile: per pair only r = E_j / (E_i + E_j), sum r and sum r^2.  The one-MUFU form works on column PAIRS
+// with the packed FP32 instructions: per two pairs FADD2 (E_i + E_j), two MUFU.RCP, FMUL2 (* E_j), FADD2 (sum r),
+// FFMA2 (sum r^2) -- 3 issue slots per pair instead of 5, which leaves the XU pipe as the only busy unit; a fixed
+// share of the slots then moves its reciprocals to the FMA pipe (rcp_newton2) to balance the two.
 template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,
                                            const float *__restrict__ sx, float cabs, bool positive,
                                            acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
+    if (MUFU1) {
+        f2_t A1[kTileRI][2], A2[kTileRI][2];
+#pragma unroll
+        for (int k = 0; k < kTileRI; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) A1[k][h] = A2[k][h] = pack2(0.0f, 0.0f);
+#pragma unroll kConstUnroll
+        for (int q = 0; q < kSubCols; q += 4) {
+            const float4 vj = *reinterpret_cast<const float4 *>(se + q);
+            const f2_t vv[2] = {pack2(vj.x, vj.y), pack2(vj.z, vj.w)};
+#pragma unroll
+            for (int k = 0; k < kTileRI; ++k) {
+                const f2_t ei = pack2(R.e[k], R.e[k]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const f2_t sum = add2(ei, vv[h]);
+                    f2_t rq;
+                    if ((ARVAE_NR_MASK >> (k * 2 + h)) & 1) {  // compile-time: a fixed subset of the 8 slots of each 4 x 4 group
+                        rq = rcp_newton2(sum);
+                    } else {
+                        float s0, s1;
+                        unpack2(sum, s0, s1);
+                        rq = pack2(rcp_approx(s0), rcp_approx(s1));
+                    }
+                    const f2_t r = mul2(rq, vv[h]);  // E_j / (E_i + E_j)
+                    A1[k][h] = add2(A1[k][h], r);
+                    if (GRAD) A2[k][h] = fma2(r, r, A2[k][h]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kTileRI; ++k) {
+            float a0, a1, a2, a3, b0, b1, b2, b3;
+            unpack2(A1[k][0], a0, a1);
+            unpack2(A1[k][1], a2, a3);
+            unpack2(A2[k][0], b0, b1);
+            unpack2(A2[k][1], b2, b3);
+            const float S1 = (a0 + a1) + (a2 + a3);
+            const float S2 = (b0 + b1) + (b2 + b3);
+            // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2)
+            acc_add(dl[k], positive ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
+            if (GRAD) acc_add(dg[k], positive ? S2 - S1 : S1 - S2);
+        }
+        return;
+    }
     float A1[kTileRI][4], A2[kTileRI][4];
 #pragma unroll
     for (int k = 0; k < kTileRI; ++k)
 #pragma unroll
         for (int q = 0; q < 4; ++q) A1[k][q] = A2[k][q] = 0.0f;
-    const float *sv = MUFU1 ? se : sx;
 #pragma unroll 2
     for (int q = 0; q < kSubCols; q += 4) {
-        const float4 vj = *reinterpret_cast<const float4 *>(sv + q);
+        const float4 vj = *reinterpret_cast<const float4 *>(sx + q);
         const float vv[4] = {vj.x, vj.y, vj.z, vj.w};
 #pragma unroll
         for (int k = 0; k < kTileRI; ++k) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float r;
-                if (MUFU1 && (k * 4 + e) >= 16 - ARVAE_NR_PAIRS) {  // compile-time: the last few pairs of each 4 x 4 group
-                    r = rcp_newton(R.e[k] + vv[e]) * vv[e];  // E_j / (E_i + E_j) without the XU pipe
-                } else {
-                    r = MUFU1 ? pair_r<true>(R.e[k], vv[e], 0.0f, cabs)
-                              : pair_r<false>(0.0f, 0.0f, R.x[k] - vv[e], cabs);
-                }
+                const float r = pair_r<false>(0.0f, 0.0f, R.x[k] - vv[e], cabs);
                 A1[k][e] += r;
                 if (GRAD) A2[k][e] = fmaf(r, r, A2[k][e]);
             }
@@ -240,7 +301,6 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
     for (int k = 0; k < kTileRI; ++k) {
         const float S1 = (A1[k][0] + A1[k][1]) + (A1[k][2] + A1[k][3]);
         const float S2 = (A2[k][0] + A2[k][1]) + (A2[k][2] + A2[k][3]);
-        // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2)
         acc_add(dl[k], positive ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
         if (GRAD) acc_add(dg[k], positive ? S2 - S1 : S1 - S2);
     }
@@ -391,11 +451,19 @@ __device__ __forceinline__ long long ceil_share(long long c, long long T, long l
     return (c * T + G - 1) / G;
 }
 
-// modelled cost (issue/MUFU cycles per 32 pairs) of one warp's 128 x 256 tile, by class and tanh form
+// modelled cost (relative time) of one warp's 128 x 256 tile, by class and tanh form; the one-MUFU constant-sign
+// tile (packed loop) is the unit = 8
+#ifndef ARVAE_COST_GENERAL1
+#define ARVAE_COST_GENERAL1 21
+#endif
+#ifndef ARVAE_COST_TIE1
+#define ARVAE_COST_TIE1 12
+#endif
 __device__ __forceinline__ int class_cost(int cls, bool mufu1) {
     // general, pos, neg, tie
-    return mufu1 ? ((0x0B08'0813u >> (8 * cls)) & 0xFF)   // 19, 8, 8, 11
-                 : ((0x1010'1014u >> (8 * cls)) & 0xFF);  // 20, 16, 16, 16
+    constexpr unsigned int k1 = (unsigned int)ARVAE_COST_GENERAL1 | (8u << 8) | (8u << 16) | ((unsigned int)ARVAE_COST_TIE1 << 24);
+    return mufu1 ? ((k1 >> (8 * cls)) & 0xFF)
+                 : ((0x1212'1216u >> (8 * cls)) & 0xFF);  // two-MUFU forms: 22, 18, 18, 18
 }
 
 // One CTA per row tile rr: class byte and cost of each of its S units (in visiting order), and the

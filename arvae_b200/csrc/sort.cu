@@ -280,8 +280,11 @@ bitonic_coop_kernel(unsigned long long *__restrict__ keys, int64_t N, KeySpec sp
 // other seven slices (copied over distributed shared memory, branch-free binary searches -- keys are unique, so the
 // count of smaller keys IS the position).  Elements are then moved, again through distributed shared memory, to the
 // CTA that owns their 1024 consecutive run positions, so that the publish to every destination buffer is a coalesced
-// stream of 16-byte stores.  ~7 us for a full run, against ~37 us for a one-CTA radix sort of the same 8192 keys:
-// eight SMs share the strided key loads and each sorts an eighth.
+// stream of 16-byte stores.  ~19 us for a full run (38k cycles: bitonic 16k, copy 3.5k, ranking 8k, publish 4k), against
+// ~37 us for a one-CTA radix sort of the same 8192 keys: eight SMs share the strided key loads and each sorts an
+// eighth.  (A variant with four keys per thread and 256-thread CTAs -- fewer shuffles and barriers, more register
+// work -- was measured slower, 40 us per sort phase against 27: with 8 warps per SM the dependent shared-memory
+// probes of the ranking are latency-bound.)
 constexpr int kClusterCtas = 8;
 constexpr int kSliceCap = kRunCap / kClusterCtas;  // 1024 keys per CTA, one per thread
 constexpr int kCsortThreads = kSliceCap;

@@ -16,11 +16,32 @@ __device__ __forceinline__ float ex2a(float x) { float y; asm volatile("ex2.appr
 __device__ __forceinline__ float rcpa(float x) { float y; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tanha(float x) { float y; asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2 -- two lanes-worth of work per issued instruction)
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pack2(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f2_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) { f2_t d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b) { f2_t d; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) { f2_t d; asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// reciprocal of two packed positive normal floats on the FMA / ALU pipes: magic seed + 3 Newton steps, all packed
+__device__ __forceinline__ f2_t rcp_newton2(f2_t x) {
+    float x0, x1;
+    unpack2(x, x0, x1);
+    f2_t y = pack2(__int_as_float(0x7EF311C7 - __float_as_int(x0)), __int_as_float(0x7EF311C7 - __float_as_int(x1)));
+    const f2_t one = pack2(1.0f, 1.0f), nx = pack2(-x0, -x1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const f2_t e = fma2(nx, y, one);
+        y = fma2(y, e, y);
+    }
+    return y;
+}
+
 constexpr int ILP = 8;
 constexpr int ITERS = 4096;
 
 template <int KIND> __global__ void rate_kernel(float *out, float seed, unsigned long long *clk);
-enum Kind { K_EX2, K_RCP, K_TANH, K_FFMA, K_FADD, K_FMNMX, K_FSET, K_PAIR_CONST, K_PAIR_CONST1, K_PAIR_GENERAL, K_EX2_RCP, K_REDUX, K_SHFL, K_F2I, K_ATOMS, K_COUNT };
+enum Kind { K_EX2, K_RCP, K_TANH, K_FFMA, K_FADD, K_FMNMX, K_FSET, K_PAIR_CONST, K_PAIR_CONST1, K_PAIR_GENERAL, K_EX2_RCP, K_REDUX, K_SHFL, K_F2I, K_ATOMS, K_FFMA2, K_FADD2, K_PAIR1_X2, K_PAIR1_X2_NR2, K_PAIR1_X2_NR3, K_COUNT };
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -60,6 +81,37 @@ __global__ void __launch_bounds__(256) rate_kernel(float *out, float seed, unsig
                 const float r = c2 * rcpa(c1 + v[k]);
                 v[k] += r;
                 w[k] = fmaf(r, r, w[k]);
+            }
+            if (KIND == K_FFMA2) {  // two FMAs per issued instruction
+                f2_t a = pack2(v[k], w[k]);
+                a = fma2(a, pack2(c1, c1), pack2(c2, c2));
+                unpack2(a, v[k], w[k]);
+            }
+            if (KIND == K_FADD2) {
+                f2_t a = pack2(v[k], w[k]);
+                a = add2(a, pack2(c1, c2));
+                unpack2(a, v[k], w[k]);
+            }
+            if (KIND == K_PAIR1_X2 || KIND == K_PAIR1_X2_NR2 || KIND == K_PAIR1_X2_NR3) {
+                // 1-MUFU constant-sign loop on TWO pairs per slot: FADD2, 2 x MUFU.RCP (or a packed Newton reciprocal
+                // for NRn of the 8 slots), FMUL2, FADD2, FFMA2
+                const int nr = KIND == K_PAIR1_X2_NR2 ? 2 : (KIND == K_PAIR1_X2_NR3 ? 3 : 0);
+                const f2_t ej = pack2(v[k], w[k]);
+                const f2_t ssum = add2(pack2(c1, c1), ej);
+                f2_t q;
+                if (k >= ILP - nr) {
+                    q = rcp_newton2(ssum);
+                } else {
+                    float s0, s1;
+                    unpack2(ssum, s0, s1);
+                    q = pack2(rcpa(s0), rcpa(s1));
+                }
+                const f2_t r = mul2(q, ej);
+                static_assert(sizeof(f2_t) == 8, "");
+                f2_t a1 = pack2(v[k], w[k]);
+                a1 = add2(a1, r);
+                a1 = fma2(r, r, a1);
+                unpack2(a1, v[k], w[k]);
             }
             if (KIND == K_PAIR_GENERAL) {    // general loop: 2 MUFU + 12
                 const float r = rcpa(ex2a(c1 - v[k]) + 1.0f);
@@ -141,6 +193,11 @@ int main(int argc, char **argv) {
             run<K_SHFL>("shfl_xor(+fadd)", 1, sms, clk_ghz, out, w),
             run<K_F2I>("f2i+i2f+fmul", 1, sms, clk_ghz, out, w),
             run<K_ATOMS>("atoms_add_8lanes_distinct", 1, sms, clk_ghz, out, w),
+            run<K_FFMA2>("ffma2_fp32_ops", 2, sms, clk_ghz, out, w),
+            run<K_FADD2>("fadd2_fp32_ops", 2, sms, clk_ghz, out, w),
+            run<K_PAIR1_X2>("pair_const_1mufu_packed_pairs", 2, sms, clk_ghz, out, w),
+            run<K_PAIR1_X2_NR2>("pair_const_packed_nr2of8_pairs", 2, sms, clk_ghz, out, w),
+            run<K_PAIR1_X2_NR3>("pair_const_packed_nr3of8_pairs", 2, sms, clk_ghz, out, w),
         };
         for (auto &r : rs) {
             printf("%s\"%s@%dw\": {\"per_clk_sm\": %.3f, \"ms\": %.4f, \"sm_ghz\": %.4f}", first ? "" : ", ", r.name, w, r.lanes_per_clk_sm, r.ms, r.ghz);
