@@ -567,6 +567,7 @@ def main():
     issue_peak_mix = ISSUE_LANES_PER_CLK_SM * sm_count * f_ghz / CONST_LOOP_INSTR_PER_PAIR
     fma_peak_mix = FP32_LANES_PER_CLK_SM * sm_count * f_ghz / CONST_LOOP_FP32_OPS_PER_PAIR
     peak_mix = min(mufu_peak_mix, issue_peak_mix, fma_peak_mix)
+    mufu_peak_2 = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / 2.0
     k_ms = (ksum.value / kn.value) if kn.value else ms_step
     pairs_per_launch = pairs / world  # this rank's rows x all columns x R
     achieved = pairs_per_launch / (k_ms * 1e-3) / 1e9
