@@ -55,7 +55,11 @@ class MeasureAttributeExtractor:
     """``extractor(measure_tensor) -> [B, 4]`` = (rhy_complexity, pitch_range, note_density, contour)."""
 
     def __init__(self, note2index: Mapping, midi_of: Callable[[str], int] = midi_from_pitch_name, device="cuda",
-                 weights: Sequence[float] = RHY_COMPLEXITY_COEFFS):
+                 weights: Sequence[float] = RHY_COMPLEXITY_COEFFS, strict: bool = True):
+        """``strict``: indices outside the note dictionary fail (a device-side assertion, no host synchronisation) --
+        the reference raises ``KeyError`` for them in pitch range / contour (bar_dataset.py:380, 489).  With
+        ``strict=False`` they are treated like the ``None`` symbol."""
+        self.strict = bool(strict)
         self.note2index_dicts = dict(note2index)
         self.lut = build_lut(note2index, midi_of).to(device)
         self.weights = torch.tensor(weights, dtype=torch.float64).float().to(device)  # .float() of the float64 table
@@ -67,6 +71,8 @@ class MeasureAttributeExtractor:
             raise RuntimeError("arvae_b200: measure_tensor must be [batch, ticks] int64")
         m = measure_tensor if measure_tensor.stride(1) == 1 else measure_tensor.contiguous()
         B, T = m.shape
+        if self.strict and B > 0:
+            torch._assert_async(((m >= 0) & (m < self.lut.numel())).all())
         if T != self.weights.numel():
             raise RuntimeError(f"arvae_b200: {T} ticks per measure but {self.weights.numel()} rhythmic weights")
         out = torch.empty((B, 4), dtype=torch.float32, device=m.device)

@@ -98,3 +98,37 @@ def test_sharded_step_matches_reference_golden(ab):
     losses, grad = _sharded(z, labels, dims, float(g["gamma"]), float(g["delta"]), 4)
     assert_loss_close(losses[0].item(), g["loss"])
     assert_grad_close(grad.cpu().numpy(), g["grad_z"][:, list(dims)])
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_buffer_entry_of_the_sharded_step(ab, pinned):
+    """arvae_shard_reg_loss_host_f32 (what bench.py's e2e leg calls on every rank) with a one-rank communicator: host
+    buffers in, host loss and dL/dz out.  With a pinned result buffer the finalize kernel writes the gradient straight
+    into host memory; with pageable memory it goes through a device buffer and a copy.  Both equal the single-GPU op."""
+    import ctypes
+    from arvae_b200 import _lib, distributed as adist, synth
+    lib = _lib.load()
+    c = synth.make_case("c4_mnist_b65536", B=9000)  # not a multiple of any tile size; two sorted runs
+    dims = tuple(c["reg_dims"])
+    z, lab = c["z"].contiguous(), c["labels"].contiguous()
+    B, Z = z.shape
+    grad = torch.full((B, Z), float("nan"))
+    if pinned:
+        z, lab, grad = z.pin_memory(), lab.pin_memory(), grad.pin_memory()
+    h = adist._ShardHandle(0, 1, B, len(dims), torch.device("cuda", torch.cuda.current_device()))
+    try:
+        for step in range(2):
+            loss = ctypes.c_float()
+            rc = lib.arvae_shard_reg_loss_host_f32(h.ctx, ctypes.c_void_p(z.data_ptr()), Z, ctypes.c_void_p(lab.data_ptr()),
+                                                   lab.shape[1], _lib.i32_array(dims), _lib.i32_array(dims), len(dims),
+                                                   _lib.i64_array([B]), c["gamma"], c["delta"], ctypes.byref(loss),
+                                                   ctypes.c_void_p(grad.data_ptr()), None)
+            _lib.check(rc, "arvae_shard_reg_loss_host_f32")
+        assert h.status() == (0, 2)
+    finally:
+        h.close()
+    zc = z.cuda().requires_grad_(True)
+    ref = ab.reg_loss_fused(zc, lab.cuda(), dims, c["gamma"], c["delta"], algo=ab.ALGO_SORTED)
+    ref.backward()
+    assert loss.value == ref.item()
+    assert torch.equal(grad, zc.grad.cpu())
