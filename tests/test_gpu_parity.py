@@ -359,6 +359,32 @@ def test_bool_and_uint8_labels_are_refused(ab):
     ab.compute_reg_loss(z, torch.zeros(8, dtype=torch.int8, device="cuda"), 0, 1.0)  # signed narrow ints are exact in f32
 
 
+def test_c5_largest_batch_properties(ab, oracle_mod):
+    """BASELINE.json C5's largest batch (B = 262 144, R = 6: 4.1e11 ordered pairs, a 256 GiB temporary in the reference):
+    sampled rows against the float64 oracle, antisymmetry, loss = sum of row sums, bitwise reproducibility."""
+    from arvae_b200 import synth
+    c = synth.make_case("c4_mnist_b65536", B=262144)
+    z, labels, B, dims = c["z"], c["labels"], c["B"], c["reg_dims"]
+    zc, lc = z.cuda(), labels.cuda()
+    loss64, grad_cols, row_loss = ab.reg_loss_rows(zc, lc, dims, c["gamma"], c["delta"], 0, B, want_row_loss=True)
+    loss_b, grad_b, _ = ab.reg_loss_rows(zc, lc, dims, c["gamma"], c["delta"], 0, B)
+    assert torch.equal(loss64, loss_b) and torch.equal(grad_cols, grad_b)
+    g = grad_cols.cpu().numpy()
+    rl = row_loss.cpu().numpy()
+    scale = np.abs(g).max(axis=0)
+    rows = np.r_[0, 8191, 8192, 131071, B - 1, np.random.RandomState(1).randint(0, B, 6)]
+    for r, dim in enumerate(dims[:3]):
+        x = z[:, dim].numpy().astype(np.float64)
+        a = labels[:, dim].numpy().astype(np.float64)
+        for i in rows:
+            _, ref_rl, ref_g = oracle_mod.reg_rows(x, a, c["delta"], int(i), int(i) + 1, f64=True)
+            assert abs(rl[i, r] - ref_rl[0]) <= 1e-6 * ref_rl[0], (i, r)
+            assert abs(g[i, r] - c["gamma"] * ref_g[0]) <= 1e-5 * scale[r], (i, r)
+    tot = rl.sum() * c["gamma"] / (float(B) * float(B))
+    assert abs(tot - loss64.item()) <= 1e-9 * tot
+    assert np.all(np.abs(g.astype(np.float64).sum(axis=0)) <= 1e-5 * scale * np.sqrt(B))
+
+
 # ------------------------------------------------------------------------------------------------
 # latent head: reparametrize + KLD (+ reg) fused
 # ------------------------------------------------------------------------------------------------

@@ -132,3 +132,14 @@ def test_host_buffer_entry_of_the_sharded_step(ab, pinned):
     ref.backward()
     assert loss.value == ref.item()
     assert torch.equal(grad, zc.grad.cpu())
+
+
+def test_full_c4_batch_eight_virtual_ranks_bitwise(ab):
+    """The benchmark configuration itself (B = 65 536, R = 6) cut over eight ranks: bitwise the single-GPU result."""
+    from arvae_b200 import synth
+    c = synth.make_case("c4_mnist_b65536")
+    zc, lc = c["z"].cuda(), c["labels"].cuda()
+    ref_loss, ref_grad = _single(ab, zc, lc, c["reg_dims"], c["gamma"], c["delta"])
+    losses, grad = _sharded(zc, lc, c["reg_dims"], c["gamma"], c["delta"], 8)
+    assert all(torch.equal(l, ref_loss) for l in losses)
+    assert torch.equal(grad, ref_grad)
