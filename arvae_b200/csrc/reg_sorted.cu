@@ -721,7 +721,10 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh);  // reg_s
 // builds and each decides on the device flag whether it is the one to run (the other exits at once).  (Both builds
 // as two instantiations of the body inside ONE kernel was measured too: 3.7 % slower than the pair of launches; ptxas's
 // schedule of the pair loops is sensitive even to the prologue -- a variant of find_unit that located both ends of the
-// range in one pass changed it and cost 2 %.)
+// range in one pass changed it and cost 2 %.  Packed-FP32 versions of the tie and general loops (263 and 374 instead of
+// 362 and 524 instructions per 32 pairs) made those tiles faster but the constant-sign loop's schedule worse: 5.38 vs
+// 5.15 ms at C4, -2 % only on tie-heavy labels; as non-inlined functions they forced 25 register moves into the
+// constant-sign loop.  Not kept.)
 template <bool GRAD, bool SIGNS, bool ONLY1>
 __global__ void __launch_bounds__(kDuoThreads, 1)
 reg_tiles_kernel(TilesArgs a) {
