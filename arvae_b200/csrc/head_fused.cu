@@ -12,7 +12,8 @@
 //   * recomputes the latent of its rows and of the columns it stages from (loc, eps, scale) -- a few hundred flops
 //     instead of a launch that materialises z first,
 //   * also handles a slice of the elementwise work (z and scale outputs, KL partial),
-//   * sweeps its pairs with the general two-MUFU loop of reg_dense.cu,
+//   * sweeps its pairs with a general loop: the one-MUFU form on packed FP32 where every sample of the tile is in
+//     range (all of delta = 1), the two-MUFU loop of reg_dense.cu otherwise,
 //   * adds its row sums into fixed-point accumulators (integer atomics: order-free, bitwise reproducible),
 // and "last CTA" tickets do the epilogues in the same launch: the last chunk of a (row block, dim) converts those
 // rows' sums into gradient columns, the last CTA of the grid reduces the loss and KL partials in index order.
@@ -63,6 +64,7 @@ template <bool GRAD>
 __global__ void __launch_bounds__(kHeadFusedThreads)
 head_fused_kernel(HeadFusedArgs a) {
     __shared__ __align__(16) float su[kSubCols];
+    __shared__ __align__(16) float se[kSubCols];
     __shared__ __align__(16) float sa[kSubCols];
     __shared__ double sred[2][kHeadFusedThreads / 32];
     __shared__ int s_last[2];
@@ -88,27 +90,76 @@ head_fused_kernel(HeadFusedArgs a) {
     const bool valid = row < a.B;
     const float xi = valid ? signed_latent(head_z(a, row * a.Z + zc), a.fsign) : 0.0f;
     const float ai = valid ? __ldg(a.lab + row * a.lrs + (int64_t)lc * a.lcs) : 0.0f;
+    // One-MUFU form r = E_j / (E_i + E_j), E = 2^(c x) (reg_sorted.cu), usable while |c x| <= 62 for every row and staged
+    // column of a tile: decided per tile by a block-wide vote (delta = 1 configs always pass; at delta = 10 a tile with
+    // an out-of-range sample runs the two-MUFU loop below).
+    const float ui = a.cabs * xi;
+    const bool row_ok = !valid || fabsf(ui) <= kMufu1MaxAbsU;
+    const float ei = exp2f(row_ok ? ui : 0.0f);
     double dl = 0.0;
     float gsum = 0.0f;
     const int64_t c0 = (int64_t)chunk * a.chunk_cols;
     const int64_t c1 = min(c0 + (int64_t)a.chunk_cols, a.Bpad);
     for (int64_t t0 = c0; t0 < c1; t0 += kSubCols) {
         __syncthreads();
+        bool col_ok = true;
         {
             const int64_t j = t0 + tid;  // kSubCols == kHeadFusedThreads: one column per thread
-            su[tid] = j < a.B ? signed_latent(head_z(a, j * a.Z + zc), a.fsign) : ARVAE_PAD_U;
+            const float xj = j < a.B ? signed_latent(head_z(a, j * a.Z + zc), a.fsign) : ARVAE_PAD_U;
+            const float uj = a.cabs * xj;
+            col_ok = j >= a.B || fabsf(uj) <= kMufu1MaxAbsU;
+            su[tid] = xj;
+            se[tid] = j < a.B ? exp2f(col_ok ? uj : 0.0f) : 8.5070592e37f;  // padding: 2^126 -> r = 1 exactly, as in reg_sorted.cu
             sa[tid] = j < a.B ? __ldg(a.lab + j * a.lrs + (int64_t)lc * a.lcs) : ARVAE_PAD_A;
         }
-        __syncthreads();
+        const bool mufu1 = __syncthreads_and(row_ok && col_ok) != 0;
         float lacc = 0.0f, gacc = 0.0f;
+        if (mufu1) {
+            // packed FP32 on column pairs: per two pairs 11 packed instructions, two MUFU.RCP, 4 FSET, 4 FMNMX.
+            // |v| is accumulated as v sgn(v); sgn(v) is the exact sign built from the attribute compares and d.
+            f2_t lacc2 = pack2(0.0f, 0.0f), gacc2 = pack2(0.0f, 0.0f);
+            const f2_t neg1 = pack2(-1.0f, -1.0f), one = pack2(1.0f, 1.0f), neg2 = pack2(-2.0f, -2.0f);
+            const f2_t bigs = pack2(1.7014118e38f, 1.7014118e38f), bigd = pack2(1.1529215e18f, 1.1529215e18f);
+            const f2_t xi2 = pack2(xi, xi), ei2 = pack2(ei, ei);
 #pragma unroll 4
-        for (int q = 0; q < kSubCols; q += 4) {
-            const float4 uj = *reinterpret_cast<const float4 *>(su + q);
-            const float4 aj = *reinterpret_cast<const float4 *>(sa + q);
-            pair_general<GRAD>(xi, ai, uj.x, aj.x, a.cabs, lacc, gacc);
-            pair_general<GRAD>(xi, ai, uj.y, aj.y, a.cabs, lacc, gacc);
-            pair_general<GRAD>(xi, ai, uj.z, aj.z, a.cabs, lacc, gacc);
-            pair_general<GRAD>(xi, ai, uj.w, aj.w, a.cabs, lacc, gacc);
+            for (int q = 0; q < kSubCols; q += 4) {
+                const float4 xj = *reinterpret_cast<const float4 *>(su + q);
+                const float4 ej = *reinterpret_cast<const float4 *>(se + q);
+                const float4 aj = *reinterpret_cast<const float4 *>(sa + q);
+                const float aa[4] = {aj.x, aj.y, aj.z, aj.w};
+                const f2_t xv[2] = {pack2(xj.x, xj.y), pack2(xj.z, xj.w)};
+                const f2_t ev[2] = {pack2(ej.x, ej.y), pack2(ej.z, ej.w)};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const f2_t d = fma2(xv[h], neg1, xi2);  // xs_i - xs_j, exact
+                    float s0, s1, q0, q1;
+                    unpack2(add2(ei2, ev[h]), s0, s1);
+                    const f2_t r = mul2(pack2(rcp_approx(s0), rcp_approx(s1)), ev[h]);
+                    const f2_t gt = pack2(ai > aa[2 * h] ? 1.0f : 0.0f, ai > aa[2 * h + 1] ? 1.0f : 0.0f);
+                    const f2_t lt = pack2(ai < aa[2 * h] ? 1.0f : 0.0f, ai < aa[2 * h + 1] ? 1.0f : 0.0f);
+                    const f2_t km1 = fma2(gt, neg1, lt);           // -s
+                    const f2_t v = fma2(neg2, r, add2(km1, one));  // t - s = (1 - s) - 2 r
+                    unpack2(fma2(km1, bigs, mul2(d, bigd)), q0, q1);
+                    const f2_t sg = pack2(fminf(fmaxf(q0, -1.0f), 1.0f), fminf(fmaxf(q1, -1.0f), 1.0f));
+                    lacc2 = fma2(v, sg, lacc2);
+                    if (GRAD) gacc2 = fma2(sg, mul2(r, fma2(r, neg1, one)), gacc2);  // sgn(v) (r - r^2)
+                }
+            }
+            float l0, l1, g0, g1;
+            unpack2(lacc2, l0, l1);
+            unpack2(gacc2, g0, g1);
+            lacc = l0 + l1;
+            gacc = g0 + g1;
+        } else {
+#pragma unroll 4
+            for (int q = 0; q < kSubCols; q += 4) {
+                const float4 uj = *reinterpret_cast<const float4 *>(su + q);
+                const float4 aj = *reinterpret_cast<const float4 *>(sa + q);
+                pair_general<GRAD>(xi, ai, uj.x, aj.x, a.cabs, lacc, gacc);
+                pair_general<GRAD>(xi, ai, uj.y, aj.y, a.cabs, lacc, gacc);
+                pair_general<GRAD>(xi, ai, uj.z, aj.z, a.cabs, lacc, gacc);
+                pair_general<GRAD>(xi, ai, uj.w, aj.w, a.cabs, lacc, gacc);
+            }
         }
         dl += (double)lacc;
         gsum += gacc;  // <= 8192 columns of |g| <= 1/4: float is ample before the fixed-point conversion below
