@@ -225,8 +225,7 @@ template <bool VALIDATE>
 __global__ void __launch_bounds__(kMergeThreads)
 runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, float *__restrict__ As,
                   float *__restrict__ Es, int *__restrict__ perm, int *__restrict__ flags, int *__restrict__ mypos,
-                  int64_t my_lo, int64_t my_hi, int64_t mypos_stride, int win_cap, PosDest pd, int blk_begin, int dbg) {
-    long long tk[6]; tk[0] = clock64();
+                  int64_t my_lo, int64_t my_hi, int64_t mypos_stride, int win_cap, PosDest pd, int blk_begin) {
     pdl_trigger();  // (sharded step) the apply kernel may start: it waits for every position by itself
     extern __shared__ __align__(16) unsigned long long dyn_smem[];  // [T][kRunPivots] pivot keys, then [win_cap] window keys
     unsigned long long *piv = dyn_smem;
@@ -282,7 +281,6 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
     if (tid == 0) s_edge[0] = key;
     if (tid == cnt - 1) s_edge[1] = key;
     __syncthreads();
-    tk[1] = clock64();
     // Window of every other run that can interleave with this CTA's keys, to pivot granularity: with j pivots below a
     // key K, K's rank in the run lies in [kPivotStep (j - 1), kPivotStep j].
     if (tid < 2 * rs.T) {
@@ -315,7 +313,6 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
     __syncthreads();
     const int total = s_total;
     const bool staged = total <= win_cap;
-    tk[2] = clock64();
     if (staged) {
         for (int i0 = tid; i0 < total; i0 += kBatch * kMergeThreads) {
             const RunElem *ptr[kBatch];
@@ -337,7 +334,6 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
         }
     }
     __syncthreads();
-    tk[3] = clock64();
     if (tid < cnt) {
         int64_t pos = p0 + tid;
         for (int o = 0; o < rs.T; ++o) {
@@ -355,9 +351,6 @@ runs_merge_kernel(RunSet rs, int64_t Bpad, float cabs, float *__restrict__ Xs, f
         }
         if (mypos && idx >= my_lo && idx < my_hi) mypos[(int64_t)r * mypos_stride + (idx - my_lo)] = (int)pos;
     }
-    if (dbg && blockIdx.x == 1 && blockIdx.y == 0 && tid == 0)
-        printf("runs_merge T=%d window %d staged %d cycles: load %lld bounds %lld stage %lld rank+write %lld\n", rs.T, total, (int)staged,
-               tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], (long long)clock64() - tk[3]);
     if (blockIdx.x == 0 && pd.n_dest == 0) count_inliers<VALIDATE>(rs, r, epoch, flags);
     // launched overlapped with the sort (sharded step): do not complete before it has, so that "this kernel is
     // complete" keeps implying "everything before it in the stream is complete" for the kernels that follow
@@ -459,13 +452,12 @@ static int launch_runs_merge(const RunSet &rs, int R, int64_t Bpad, float cabs, 
     if (n_blk < 0) n_blk = (int)(rs.blk_off[rs.T] + ceil_div(Bpad - B, kMergeThreads));
     if (n_blk == 0) return 0;
     dim3 grid((unsigned)n_blk, (unsigned)R);
-    static const int dbg = getenv("ARVAE_DEBUG_PHASES") ? 1 : 0;
     if (rs.epoch_ctr)  // sharded step: overlapped with the sort kernel before it (every load validates itself)
         ARVAE_CUDA_TRY(launch_kernel(runs_merge_kernel<true>, grid, dim3(kMergeThreads), smem, st, true, rs, Bpad, cabs, Xs, As, Es, perm,
-                                     flags, mypos, my_lo, my_hi, mypos_stride, win_cap, pd, blk_begin, dbg));
+                                     flags, mypos, my_lo, my_hi, mypos_stride, win_cap, pd, blk_begin));
     else
         runs_merge_kernel<false><<<grid, kMergeThreads, smem, st>>>(rs, Bpad, cabs, Xs, As, Es, perm, flags, mypos, my_lo, my_hi,
-                                                                 mypos_stride, win_cap, pd, blk_begin, dbg);
+                                                                 mypos_stride, win_cap, pd, blk_begin);
     ARVAE_LAUNCH_CHECK("runs_merge_kernel");
     return 0;
 }
@@ -509,19 +501,30 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh /* shared m
 // ------------------------------------------------------------------------------------------------------------
 // (C) finalize: pull this rank's row sums and every rank's loss partial
 // ------------------------------------------------------------------------------------------------------------
-// Row sum of sample i (local index) of dim r, pulled from the accumulators of the 1-2 ranks that swept its sorted
-// position, as a gradient element (NaN where the reference's float arithmetic gives NaN).
-__device__ __forceinline__ float shard_pull_grad(const TilesArgs &a, const ShardView &v, const int *__restrict__ mypos, int r,
-                                                 int64_t i, double gscale) {
+// Where the row sum of sample i (local index) of dim r lives: accumulator index and the 1-2 ranks that swept its sorted
+// position.  Depends on the plan only, so it is worked out BEFORE the wait for the peers.
+struct ShardRowRef {
+    int64_t slot;   // rr * kTileRows + position within the row tile
+    int h0, h1;
+    bool poisoned;  // the reference's float arithmetic gives NaN for this row
+};
+__device__ __forceinline__ ShardRowRef shard_locate_row(const TilesArgs &a, const ShardView &v, const int *__restrict__ mypos,
+                                                        int r, int64_t i) {
     const int64_t pos = mypos[(int64_t)r * v.n_cap + i];
     const int64_t rr = (int64_t)r * a.n_row_tiles + pos / kTileRows;
     const long long T = a.prefix[a.n_rr];
-    const int h0 = (int)(owner_of_pos(a.prefix[rr], T, a.G) / v.Gc);
-    const int h1 = (int)(owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G) / v.Gc);
+    ShardRowRef ref;
+    ref.slot = rr * kTileRows + pos % kTileRows;
+    ref.h0 = (int)(owner_of_pos(a.prefix[rr], T, a.G) / v.Gc);
+    ref.h1 = (int)(owner_of_pos(a.prefix[rr + 1] - (long long)a.cost8[rr * a.S + a.S - 1], T, a.G) / v.Gc);
+    ref.poisoned = row_is_poisoned(a.flags, r, a.Xs[(int64_t)r * a.Bpad + pos]);
+    return ref;
+}
+__device__ __forceinline__ float shard_pull_grad(const ShardView &v, const ShardRowRef &ref, double gscale, bool broken) {
+    if (broken || ref.poisoned) return __int_as_float(0x7fc00000);
     acc_t g = 0;
-    for (int h = h0; h <= h1; ++h) g += ld_relaxed_sys_s64(shard_acc(v, h) + rr * kTileRows + pos % kTileRows);
-    const bool poisoned = row_is_poisoned(a.flags, r, a.Xs[(int64_t)r * a.Bpad + pos]);
-    return poisoned ? __int_as_float(0x7fc00000) : (float)((double)g * kFixScale * gscale);
+    for (int h = ref.h0; h <= ref.h1; ++h) g += ld_relaxed_sys_s64(shard_acc(v, h) + ref.slot);
+    return (float)((double)g * kFixScale * gscale);
 }
 
 // Outputs: grad_cols [n, R] (one thread per element), or -- the host-buffer entry -- grad_z [n, Z] with the scatter
@@ -533,23 +536,42 @@ shard_finalize_kernel(TilesArgs a, const int *__restrict__ mypos, int R, double 
                       RegDims dims) {
     const ShardView &v = a.shard;
     ShardHeader *hdr = shard_header(v, v.g);
-    pdl_wait();  // launched ahead of the pair kernel's end: sleep until it is complete, then wait for the peers
+    pdl_wait();  // everything this rank produced (plan, positions, its pair kernel) is complete
     const unsigned long long epoch = hdr->epoch + 1;
-    shard_wait(v, epoch);
     const int64_t n = v.row_off[v.g + 1] - v.row_off[v.g];
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool broken = *reinterpret_cast<volatile int *>(&hdr->status) != 0;  // a wait gave up: positions may be garbage
-    if (grad_z) {  // over n * Z, column fastest
+    // locate this thread's row sum(s) first, then wait for the peers, then pull over NVLink
+    ShardRowRef ref;
+    ref.slot = -1;
+    ref.h0 = 0; ref.h1 = -1; ref.poisoned = false;
+    const bool broken_early = *reinterpret_cast<volatile int *>(&hdr->status) != 0;  // an earlier wait of this step gave up: the
+                                                                                    // positions may be garbage, do not use them
+    if (broken_early) {
+    } else if (grad_z) {  // over n * Z, column fastest: the (at most one, in practice) regularised dim of this latent column
         if (idx < n * Z) {
             const int zc = (int)(idx % Z);
-            const int64_t i = idx / Z;
-            float g = 0.0f;
             for (int r = 0; r < R; ++r)
-                if (dims.zcol[r] == zc) g += broken ? __int_as_float(0x7fc00000) : shard_pull_grad(a, v, mypos, r, i, gscale);
-            grad_z[idx] = g;
+                if (dims.zcol[r] == zc && ref.slot < 0) ref = shard_locate_row(a, v, mypos, r, idx / Z);
         }
     } else if (grad_cols && idx < n * R) {  // over n * R, dim fastest (coalesced stores)
-        grad_cols[idx] = broken ? __int_as_float(0x7fc00000) : shard_pull_grad(a, v, mypos, (int)(idx % R), idx / R, gscale);
+        ref = shard_locate_row(a, v, mypos, (int)(idx % R), idx / R);
+    }
+    shard_wait(v, epoch);
+    const bool broken = *reinterpret_cast<volatile int *>(&hdr->status) != 0;  // a wait gave up: positions may be garbage
+    if (grad_z) {
+        if (idx < n * Z) {
+            float g = ref.slot >= 0 ? shard_pull_grad(v, ref, gscale, broken) : (broken ? __int_as_float(0x7fc00000) : 0.0f);
+            const int zc = (int)(idx % Z);
+            bool first = true;
+            for (int r = 0; r < R; ++r) {  // a latent column regularised by several attributes (not a reference configuration)
+                if (dims.zcol[r] != zc) continue;
+                if (!first && !broken) g += shard_pull_grad(v, shard_locate_row(a, v, mypos, r, idx / Z), gscale, broken);
+                first = false;
+            }
+            grad_z[idx] = g;
+        }
+    } else if (grad_cols && idx < n * R) {
+        grad_cols[idx] = shard_pull_grad(v, ref, gscale, broken);
     }
     if (blockIdx.x == 0) {
         __shared__ acc_t shl[2][kMaxShardRanks];

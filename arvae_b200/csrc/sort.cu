@@ -465,8 +465,7 @@ __device__ __forceinline__ int count_below_pow2(const unsigned long long *__rest
 }
 
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kCsortThreads, 1)
-cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, const unsigned long long *__restrict__ epoch_ctr, int dbg) {
-    long long tk[8]; tk[0] = clock64();
+cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, const unsigned long long *__restrict__ epoch_ctr) {
     pdl_trigger();  // a sharded step's ranking kernel may start now: it waits for every run element by itself
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CsortSmem &S = *reinterpret_cast<CsortSmem *>(smem_raw);
@@ -474,7 +473,7 @@ cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, 
     const int c = (int)cluster.block_rank();
     const int run = (int)blockIdx.x / kClusterCtas;
     const int r = blockIdx.y;
-    const int t = threadIdx.x, lane = t & 31;
+    const int t = threadIdx.x;
     const int64_t j0 = (int64_t)run * kRunCap;                      // first local sample of this run
     const int n = (int)min((int64_t)kRunCap, n_total - j0);        // >= 1 by construction of the grid
     int M = 32;                                                     // slice length: next power of two of ceil(n / 8)
@@ -487,7 +486,6 @@ cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, 
         S.xs[t] = xs;
         v = sort_key_from(spec, a, xs, j0 + i_local);
     }
-    tk[1] = clock64();
     // bitonic network over the M keys of the slice (threads >= M only keep the barriers company)
     for (int k = 2; k <= M; k <<= 1) {
         for (int j = k >> 1; j >= 1; j >>= 1) {
@@ -505,9 +503,7 @@ cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, 
         }
     }
     S.own[t] = v;  // threads >= M hold padding (their partners, t ^ j with j < M, are >= M too)
-    tk[2] = clock64();
     cluster.sync();
-    tk[3] = clock64();
     // the other slices, in cluster-rank order with this CTA skipped
 #pragma unroll
     for (int q = 0; q < kClusterCtas - 1; ++q) {
@@ -516,7 +512,6 @@ cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, 
         if (t < M) S.others[q][t] = remote[t];
     }
     __syncthreads();
-    tk[4] = clock64();
     const bool real = v != ~0ull;
     if (real) {
         int p = t;  // rank inside the own slice
@@ -531,9 +526,7 @@ cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, 
         uint4 *remote_out = cluster.map_shared_rank(S.out, p / kSliceCap);
         remote_out[p % kSliceCap] = e;
     }
-    tk[5] = clock64();
     cluster.sync();
-    tk[6] = clock64();
     // publish run positions [1024 c, 1024 (c + 1)): one 16-byte store per element and destination
     const int p = c * kSliceCap + t;
     if (p < n) {
@@ -544,10 +537,6 @@ cluster_sort_kernel(KeySpec spec, int64_t n_total, int first_run, RunDest dest, 
             if (p % kPivotStep == 0) slot[kRunCap + p / kPivotStep] = e;  // pivot copy
         }
     }
-    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && t == 0)
-        printf("cluster_sort n=%d M=%d cycles: keys %lld bitonic %lld csync %lld copy %lld rank+scatter %lld csync %lld publish %lld\n", n, M,
-               tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], (long long)clock64() - tk[6]);
-    (void)lane;
 }
 
 int run_chunk_sort(const KeySpec &spec, int R, int64_t n, int first_run, const RunDest &dest,
@@ -571,8 +560,7 @@ int run_chunk_sort(const KeySpec &spec, int R, int64_t n, int first_run, const R
         return 0;
     }
     dim3 grid((unsigned)(runs * kClusterCtas), (unsigned)R);
-    static const int dbg = getenv("ARVAE_DEBUG_PHASES") ? 1 : 0;
-    cluster_sort_kernel<<<grid, kCsortThreads, sizeof(CsortSmem), st>>>(spec, n, first_run, dest, epoch_ctr, dbg);
+    cluster_sort_kernel<<<grid, kCsortThreads, sizeof(CsortSmem), st>>>(spec, n, first_run, dest, epoch_ctr);
     ARVAE_LAUNCH_CHECK("cluster_sort_kernel");
     return 0;
 }
