@@ -576,6 +576,10 @@ int arvae_shard_create(int32_t rank, int32_t world, int64_t n_cap, int32_t R_cap
         set_error("bad argument to shard_create (world <= %d, R_cap <= %d)", kMaxShardRanks, ARVAE_MAX_REG_DIMS);
         return ARVAE_E_BADARG;
     }
+    if (const char *w = getenv("ARVAE_SHARD_WAIT_MS")) {
+        int rc = shard_set_wait_ms(atoll(w));
+        if (rc) return rc;
+    }
     ShardCtx *C = new ShardCtx();
     C->G = world; C->g = rank; C->R_cap = R_cap; C->n_cap = n_cap;
     cudaError_t e = cudaGetDevice(&C->device);

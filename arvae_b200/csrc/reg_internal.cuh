@@ -219,6 +219,7 @@ struct ShardStep {
 size_t shard_comm_bytes(int64_t n_cap, int R_cap, int G, ShardCtx *fill);
 size_t shard_ws_bytes(int64_t n_cap, int R_cap, int G, size_t *off_mypos);
 int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st);
+int shard_set_wait_ms(long long ms);  // bound of every wait for a peer on the current device (default 30 s)
 
 // pairwise-rank evaluation metrics (eval_metrics.cu)
 constexpr int kEvalMaxCodes = 1024, kEvalMaxAttrs = 64;

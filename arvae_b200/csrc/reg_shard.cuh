@@ -57,7 +57,10 @@ __device__ __forceinline__ acc_t *shard_acc(const ShardView &v, int h) {
     return reinterpret_cast<acc_t *>(v.peer[h] + v.off_acc);
 }
 
-constexpr unsigned long long kShardWaitNs = 4000000000ull;  // 4 s: far beyond any healthy step
+// Longest a kernel waits for a peer (element, position or flag) before it gives up, marks the communicator broken and
+// lets the step end with NaN results instead of hanging the GPU.  30 s by default -- ranks of a training job drift (data
+// loading, checkpoints) -- and ARVAE_SHARD_WAIT_MS at arvae_shard_create overrides it.
+__constant__ unsigned long long kShardWaitNs = 30000000000ull;
 
 // Threads 0..G-1 of the CTA each wait for one peer's flag B to reach `epoch`; everybody leaves together.
 __device__ __forceinline__ void shard_wait(const ShardView &v, unsigned long long epoch) {
@@ -604,6 +607,12 @@ shard_finalize_kernel(TilesArgs a, const int *__restrict__ mypos, int R, double 
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+int shard_set_wait_ms(long long ms) {
+    const unsigned long long ns = (unsigned long long)(ms > 0 ? ms : 1) * 1000000ull;
+    ARVAE_CUDA_TRY(cudaMemcpyToSymbol(kShardWaitNs, &ns, sizeof(ns)));
+    return 0;
+}
+
 static int shard_runs_cap(int64_t n_cap, int G) {
     const int64_t t = (int64_t)G * ceil_div(n_cap, kRunCap);
     return (int)(t < kMaxRuns ? t : kMaxRuns);

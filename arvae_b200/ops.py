@@ -49,7 +49,9 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"arvae_b200: {name} must be a CUDA tensor (no CPU fallback exists for this path)")
     if t.dtype != torch.float32:
-        raise RuntimeError(f"arvae_b200: {name} must be float32, got {t.dtype}")
+        hint = (' (set arvae_b200.ops.FLOAT64_POLICY = "compute_in_float32" to have float64 latents rounded to float32 '
+                'and the results returned as float64)') if t.dtype == torch.float64 else ""
+        raise RuntimeError(f"arvae_b200: {name} must be float32, got {t.dtype}{hint}")
 
 
 def _scalar(v) -> float:
@@ -190,12 +192,22 @@ def _normalize_dims(reg_dims: Sequence[int], Z: int) -> Tuple[int, ...]:
     return tuple(out)
 
 
+# float64 latents: the reference returns a float64 result computed in float64 (utils/trainer.py:374-376).  This path's
+# arithmetic type is float32 (BASELINE.json north_star), so by default float64 is refused rather than silently narrowed;
+# set ``arvae_b200.ops.FLOAT64_POLICY = "compute_in_float32"`` to accept it: the latents are rounded to float32, the loss
+# and gradient come back as float64 tensors (the reference's dtype contract) with float32 accuracy (~1e-7 relative).
+FLOAT64_POLICY = "raise"
+
+
 def _upcast_half(z: torch.Tensor):
     """float16 / bfloat16 latents (autocast) are computed in float32 -- strictly more accurate than the reference's
     half-precision op chain -- and the result is cast back to the input dtype, as the reference's would be.
-    float64 is NOT silently narrowed: it raises in _require_cuda_f32."""
-    if isinstance(z, torch.Tensor) and z.is_cuda and z.dtype in (torch.float16, torch.bfloat16):
-        return z.float(), z.dtype
+    float64 is NOT silently narrowed: it raises in _require_cuda_f32 unless FLOAT64_POLICY says otherwise."""
+    if isinstance(z, torch.Tensor) and z.is_cuda:
+        if z.dtype in (torch.float16, torch.bfloat16):
+            return z.float(), z.dtype
+        if z.dtype == torch.float64 and FLOAT64_POLICY == "compute_in_float32":
+            return z.float(), z.dtype
     return z, None
 
 

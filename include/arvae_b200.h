@@ -234,7 +234,10 @@ ARVAE_API int arvae_pack_columns_f32(const float *z_dev, int64_t z_row_stride, i
  *                             runs / apply+plan+pairs / finalize (tests drive several ranks of one process through
  *                             the phases in lockstep).
  *                             Stream-ordered, no host sync, no NCCL.  A peer that never shows up makes the loss NaN
- *                             after a bounded wait (arvae_shard_status reports it) instead of hanging the GPU.
+ *                             after a bounded wait (30 s; environment variable ARVAE_SHARD_WAIT_MS, read by
+ *                             arvae_shard_create, overrides it; arvae_shard_status reports it) instead of hanging
+ *                             the GPU.  A communicator whose wait gave up stays broken (every later step is NaN):
+ *                             destroy it and create a new one.
  *   arvae_shard_reg_loss_host_f32  the same with HOST buffers in and out (H2D, step, dL/dz scatter, D2H, sync).
  */
 #define ARVAE_SHARD_HANDLE_BYTES 64

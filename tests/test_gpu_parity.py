@@ -688,3 +688,15 @@ def test_half_precision_latents_are_upcast_and_float64_is_refused(ab):
         assert one.dtype == dt
     with pytest.raises(RuntimeError, match="float32"):
         ab.reg_loss_fused(dev(g["z"]).double(), labels, dims, 1.0, 1.0)
+    # opt-in: float64 latents rounded to float32, results returned as float64 like the reference's (utils/trainer.py:374-376)
+    from arvae_b200 import ops
+    ops.FLOAT64_POLICY = "compute_in_float32"
+    try:
+        z64 = dev(g["z"]).double().requires_grad_(True)
+        loss64 = ab.reg_loss_fused(z64, labels, dims, float(g["gamma"]), float(g["delta"]))
+        loss64.backward()
+        assert loss64.dtype == torch.float64 and z64.grad.dtype == torch.float64
+        assert_loss_close(loss64.item(), g["loss"])
+        assert_grad_close(z64.grad.cpu().numpy(), g["grad_z"])
+    finally:
+        ops.FLOAT64_POLICY = "raise"

@@ -143,3 +143,30 @@ def test_full_c4_batch_eight_virtual_ranks_bitwise(ab):
     losses, grad = _sharded(zc, lc, c["reg_dims"], c["gamma"], c["delta"], 8)
     assert all(torch.equal(l, ref_loss) for l in losses)
     assert torch.equal(grad, ref_grad)
+
+
+def test_a_peer_that_never_shows_up_gives_nan_after_a_bounded_wait(ab):
+    """Failure detection of the sharded step: rank 0 runs its whole step while rank 1 never publishes.  Its kernels give
+    up after the wait bound (ARVAE_SHARD_WAIT_MS), the communicator reports status 1, loss and gradient are NaN -- the
+    GPU is not hung."""
+    import os
+    from arvae_b200 import distributed as adist, synth
+    c = synth.make_case("c4_mnist_b65536", B=2048)
+    dims = tuple(c["reg_dims"])
+    z, lab = c["z"].cuda(), c["labels"].cuda()
+    os.environ["ARVAE_SHARD_WAIT_MS"] = "100"
+    try:
+        grp = adist.LocalShardGroup(2, 1024, len(dims))
+        try:
+            h = grp.ranks[0]
+            loss64, loss32, grad = h.step(z[:1024], lab[:1024], dims, dims, [1024, 1024], c["gamma"], c["delta"], True, 0)
+            torch.cuda.synchronize()
+            status, epoch = h.status()
+            assert status == 1
+            assert torch.isnan(loss64) and torch.isnan(grad).all()
+        finally:
+            grp.close()
+    finally:
+        os.environ["ARVAE_SHARD_WAIT_MS"] = "30000"
+        adist.LocalShardGroup(1, 16, 1).close()  # restores the default bound for the rest of the process
+        del os.environ["ARVAE_SHARD_WAIT_MS"]
