@@ -483,7 +483,8 @@ plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost, int clear_acc, un
     __shared__ float wmin[kTileThreads / 32], wmax[kTileThreads / 32];
     __shared__ int whas[kTileThreads / 32], win[kTileThreads / 32], wmixed[kTileThreads / 32];
     __shared__ int sred[8];
-    pdl_wait();  // (sharded step: launched ahead of the apply kernel's end) the sorted columns must be complete
+    pdl_wait();     // (sharded step: launched ahead of the apply kernel's end) the sorted columns must be complete
+    pdl_trigger();  // the pair kernel's CTAs may be placed as SMs free up; they wait for this grid to complete
     const int64_t rr = blockIdx.x;
     const int r = (int)(rr / a.n_row_tiles), I = (int)(rr % a.n_row_tiles);
     const float *Ar = a.As + (int64_t)r * a.Bpad;
@@ -735,6 +736,7 @@ reg_tiles_kernel(TilesArgs a) {
     __shared__ unsigned int s_claimed;   // units granted so far (may overshoot N)
     __shared__ int s_grant[2][2];        // per half: first unit (linear) and count of the current grant
 
+    pdl_wait();  // launched ahead of the plan kernel's end (programmatic dependent launch): wait for the plan
     if (a.dual && (a.flags[kFlagAnyTwoMufu] != 0) == ONLY1) return;  // the other build's turn
     const long long c = (long long)a.c_first + blockIdx.x;
     if (a.dbg_times && threadIdx.x == 0) {
@@ -979,18 +981,19 @@ static int tiles_ctas_per_sm() {
 }
 
 static void launch_tiles(TilesArgs a, int n_cta, bool want_grad, bool want_signs, cudaStream_t st) {
+    const dim3 grid((unsigned)n_cta), block(kDuoThreads);
     if (want_signs) {  // parity instrumentation: the complete build only
         a.dual = 0;
-        reg_tiles_kernel<true, true, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+        launch_kernel(reg_tiles_kernel<true, true, false>, grid, block, kDuoStageBytes, st, true, a);
         return;
     }
     a.dual = 1;  // both builds; the device flag decides which one works
     if (want_grad) {
-        reg_tiles_kernel<true, false, true><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
-        reg_tiles_kernel<true, false, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+        launch_kernel(reg_tiles_kernel<true, false, true>, grid, block, kDuoStageBytes, st, true, a);
+        launch_kernel(reg_tiles_kernel<true, false, false>, grid, block, kDuoStageBytes, st, true, a);
     } else {
-        reg_tiles_kernel<false, false, true><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
-        reg_tiles_kernel<false, false, false><<<n_cta, kDuoThreads, kDuoStageBytes, st>>>(a);
+        launch_kernel(reg_tiles_kernel<false, false, true>, grid, block, kDuoStageBytes, st, true, a);
+        launch_kernel(reg_tiles_kernel<false, false, false>, grid, block, kDuoStageBytes, st, true, a);
     }
     count_launch();
 }
