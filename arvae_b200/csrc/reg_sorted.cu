@@ -1,7 +1,7 @@
 // reg_sorted.cu -- attribute-sorted pair kernel (sm_100a): the fast path for large batches.
 //
 // Same arithmetic as reg_dense.cu (reference utils/trainer.py:390-401 and its autograd backward),
-// reorganised so that almost every pair costs 1 MUFU + 4 FP32 instructions instead of 2 + 12:
+// reorganised so that almost every pair costs 0.63 MUFU + 2.4 packed FP32 instructions instead of 2 + 12:
 //
 //  * rows and columns of each regularised dim are ordered by attribute value (sort.cu).  A tile of
 //    128 rows (one warp) x 256 columns whose attribute ranges do not overlap has a CONSTANT sign s_ij, so per
@@ -13,7 +13,7 @@
 //    straddle the diagonal band / a tie-group edge run the general loop with per-pair float
 //    compares of the raw attributes -- the sign is exact by construction in all three classes.
 //  * r = 1/(1 + 2^(u_i-u_j)) = E_j / (E_i + E_j) with u = 2 f log2(e) x and E = 2^u precomputed once
-//    per element: one MUFU.RCP per pair.  Safe while |u| <= 62 for every element of the dim (no
+//    per element: one MUFU.RCP per pair (the constant-sign loop evaluates 1 - r = 1 / (1 + E_j F_i), F_i = 2^-u_i per row).  Safe while |u| <= 62 for every element of the dim (no
 //    overflow in E_i+E_j, full relative accuracy in both saturation directions); a per-dim flag
 //    computed by the gather kernel falls back to the 2-MUFU form (EX2 + RCP on the scaled latent
 //    difference) otherwise.
@@ -176,48 +176,68 @@ __device__ __forceinline__ void acc_add(acc_t &acc, float v) {
 // Per-thread row operands of one row tile.
 struct RowRegs {
     float e[kTileRI];  // 2^u_i          (1-MUFU form)
+    float f[kTileRI];  // 2^-u_i         (1-MUFU form of the constant-sign loop, ARVAE_PAIR_FORM 1)
     float x[kTileRI];  // sgn(f) x_i     (2-MUFU form, exact tie signs)
     float a[kTileRI];  // attribute
 };
 
-// Reciprocal on the FMA / ALU pipes: magic-constant seed (relative error < 0.051) and three Newton steps
-// (error -> 2.6e-3 -> 6.8e-6 -> 4.6e-11, i.e. correctly rounded to within an ulp).  7 instructions instead of one
-// MUFU.RCP: used for a small, fixed subset of the pairs of the constant-sign loop so that the XU pipe (the
-// bound) and the issue slots (idle ~35 % of the time) are both kept busy.  Valid for normal positive x.
-__device__ __forceinline__ float rcp_newton(float x) {
-    float y = __int_as_float(0x7EF311C7 - __float_as_int(x));
-    float e = fmaf(-x, y, 1.0f);
-    y = fmaf(y, e, y);
-    e = fmaf(-x, y, 1.0f);
-    y = fmaf(y, e, y);
-    e = fmaf(-x, y, 1.0f);
-    return fmaf(y, e, y);
-}
-
-// The same on two packed values (FFMA2: one issued instruction per Newton step for two reciprocals).
+// Reciprocal on the FMA pipe for a fixed share of the pairs of the constant-sign loop, so that the XU pipe (MUFU.RCP,
+// 16 lanes/clk/SM) and the FP32 pipe are both kept busy: magic-constant seed (relative error < 0.051), one quadratic
+// Newton step (-> 2.6e-3) and one cubic step y (1 + e + e^2) (-> 1.8e-8; measured over 3e6 arguments in [1, 2^124]:
+// 1.28 * 2^-24, within an ulp like MUFU.RCP itself) -- five FFMA2 and two IADD per TWO reciprocals.  ARVAE_NR_OPS 6
+// keeps round 2's three quadratic steps (4.6e-11 before rounding; 4.73 instead of 4.53 ms at C4).  Valid for normal
+// positive x below 2^126.
+#ifndef ARVAE_NR_OPS
+#define ARVAE_NR_OPS 5
+#endif
 __device__ __forceinline__ f2_t rcp_newton2(f2_t x) {
     float x0, x1;
     unpack2(x, x0, x1);
     f2_t y = pack2(__int_as_float(0x7EF311C7 - __float_as_int(x0)), __int_as_float(0x7EF311C7 - __float_as_int(x1)));
     const f2_t one = pack2(1.0f, 1.0f), nx = pack2(-x0, -x1);
+#if ARVAE_NR_OPS == 5
+    f2_t e = fma2(nx, y, one);
+    y = fma2(y, e, y);
+    e = fma2(nx, y, one);
+    const f2_t t = fma2(e, e, e);
+    return fma2(y, t, y);
+#else
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const f2_t e = fma2(nx, y, one);
         y = fma2(y, e, y);
     }
     return y;
+#endif
 }
 
+// Form of the one-MUFU constant-sign loop:
+//   0   r = E_j / (E_i + E_j):          FADD2, two RCP, FMUL2, then the two accumulations     (4 FP32 per two pairs)
+//   1   q = 1 - r = 1 / (1 + E_j F_i):  FFMA2, two RCP, then the two accumulations            (3 FP32 per two pairs)
+//       with F_i = 2^-u_i held per row.  r - r^2 = q - q^2, so the gradient sums are the same expression and only the
+//       two loss expressions swap; 1 + E_j F_i <= 1 + 2^124 for inliers (|u| <= 62).
+// ARVAE_NR_MASK: which of the 16 (column group g, row k, column pair h) slots (bit 8 g + 2 k + h) of a 4 x 8 pair group
+// take their two reciprocals from rcp_newton2 instead of two MUFU.RCP.  ptxas's schedule decides, not the count alone:
+// pair kernel on C4, ms --
+//   form 0 (6-op Newton): no slot 5.86 (scalar loop), 2 of 16 5.48, 4 of 16 (0xC0C0) 5.15, 6 of 16 5.51
+//   form 1, 6-op Newton:  0xC0C0 4.73, 0xC0E0 5.28, 0xE0E0 5.06
+//   form 1, 5-op Newton:  0xE0E0 4.53 (kept), 0xD0D0 4.54, 0xA0E0 4.55, 0x00FC 4.60, 0xA8A8 4.62, 0xE00E 4.65, 0x3838 4.67,
+//                         0xB0B0 4.67, 0x0E0E 4.68, 0xE0E1 4.68, 0x5454 4.71, 0x8383 4.74, 0x0707 4.75, 0x7070 4.77,
+//                         0xE0F0 4.80, 0xC1C1 4.87, 0xE8E0 4.88, 0xC0E0 5.00, 0xE0C0 5.07; unrolling the group loop twice: same
+#ifndef ARVAE_PAIR_FORM
+#define ARVAE_PAIR_FORM 1
+#endif
 #ifndef ARVAE_NR_MASK
-#define ARVAE_NR_MASK 0xC0  // which of the 8 (row k, column pair h) slots (bit 2 k + h) of a 4 x 4 pair group of the one-MUFU
-                            // constant-sign loop take their two reciprocals from rcp_newton2 (FMA pipe) instead of two
-                            // MUFU.RCP (XU pipe).  Pair kernel on C4, ms: no slot 5.86 (scalar loop), one slot 5.48, two
-                            // slots (0xC0) 5.15, three 5.51
+#if ARVAE_PAIR_FORM == 1
+#define ARVAE_NR_MASK 0xE0E0
+#else
+#define ARVAE_NR_MASK 0xC0C0
 #endif
-#ifndef ARVAE_CONST_UNROLL
-#define ARVAE_CONST_UNROLL 2
 #endif
-constexpr int kConstUnroll = ARVAE_CONST_UNROLL;
+#ifndef ARVAE_CONST_OUTER_UNROLL
+#define ARVAE_CONST_OUTER_UNROLL 1
+#endif
+constexpr int kConstOuterUnroll = ARVAE_CONST_OUTER_UNROLL;
 
 template <bool MUFU1>
 __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs) {
@@ -225,10 +245,10 @@ __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs)
     return rcp_approx(ex2_approx(d * cabs) + 1.0f);       // 1 / (1 + 2^(|c| (xs_i - xs_j)))
 }
 
-// Constant-sign tile: per pair only r = E_j / (E_i + E_j), sum r and sum r^2.  The one-MUFU form works on column PAIRS
-// with the packed FP32 instructions: per two pairs FADD2 (E_i + E_j), two MUFU.RCP, FMUL2 (* E_j), FADD2 (sum r),
-// FFMA2 (sum r^2) -- 3 issue slots per pair instead of 5, which leaves the XU pipe as the only busy unit; a fixed
-// share of the slots then moves its reciprocals to the FMA pipe (rcp_newton2) to balance the two.
+// Constant-sign tile: per pair only q = 1 - r = 1 / (1 + E_j F_i), sum q and sum q^2.  The one-MUFU form works on column
+// PAIRS with the packed FP32 instructions: per two pairs FFMA2 (1 + E_j F_i), two MUFU.RCP (or, on 6 of 16 slots, the packed
+// Newton reciprocal on the FMA pipe), FADD2 (sum q), FFMA2 (sum q^2).  SASS of the loop: 118 instructions per 32 pairs
+// (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128): XU pipe 160 and FP32 pipe 156 clk per warp iteration.
 template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,
                                            const float *__restrict__ sx, float cabs, bool positive,
@@ -239,27 +259,32 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
         for (int k = 0; k < kTileRI; ++k)
 #pragma unroll
             for (int h = 0; h < 2; ++h) A1[k][h] = A2[k][h] = pack2(0.0f, 0.0f);
-#pragma unroll kConstUnroll
-        for (int q = 0; q < kSubCols; q += 4) {
-            const float4 vj = *reinterpret_cast<const float4 *>(se + q);
-            const f2_t vv[2] = {pack2(vj.x, vj.y), pack2(vj.z, vj.w)};
+        const f2_t one = pack2(1.0f, 1.0f);
+#pragma unroll kConstOuterUnroll
+        for (int q = 0; q < kSubCols; q += 8) {
 #pragma unroll
-            for (int k = 0; k < kTileRI; ++k) {
-                const f2_t ei = pack2(R.e[k], R.e[k]);
+            for (int g = 0; g < 2; ++g) {
+                const float4 vj = *reinterpret_cast<const float4 *>(se + q + 4 * g);
+                const f2_t vv[2] = {pack2(vj.x, vj.y), pack2(vj.z, vj.w)};
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const f2_t sum = add2(ei, vv[h]);
-                    f2_t rq;
-                    if ((ARVAE_NR_MASK >> (k * 2 + h)) & 1) {  // compile-time: a fixed subset of the 8 slots of each 4 x 4 group
-                        rq = rcp_newton2(sum);
-                    } else {
-                        float s0, s1;
-                        unpack2(sum, s0, s1);
-                        rq = pack2(rcp_approx(s0), rcp_approx(s1));
+                for (int k = 0; k < kTileRI; ++k) {
+                    const f2_t ri = ARVAE_PAIR_FORM == 1 ? pack2(R.f[k], R.f[k]) : pack2(R.e[k], R.e[k]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        // form 0: E_i + E_j;  form 1: 1 + E_j F_i = (E_i + E_j) / E_i
+                        const f2_t sum = ARVAE_PAIR_FORM == 1 ? fma2(vv[h], ri, one) : add2(ri, vv[h]);
+                        f2_t rq;
+                        if ((ARVAE_NR_MASK >> (g * 8 + k * 2 + h)) & 1) {  // compile-time: a fixed subset of the 16 slots
+                            rq = rcp_newton2(sum);
+                        } else {
+                            float s0, s1;
+                            unpack2(sum, s0, s1);
+                            rq = pack2(rcp_approx(s0), rcp_approx(s1));
+                        }
+                        const f2_t r = ARVAE_PAIR_FORM == 1 ? rq : mul2(rq, vv[h]);  // form 0: r;  form 1: 1 - r
+                        A1[k][h] = add2(A1[k][h], r);
+                        if (GRAD) A2[k][h] = fma2(r, r, A2[k][h]);
                     }
-                    const f2_t r = mul2(rq, vv[h]);  // E_j / (E_i + E_j)
-                    A1[k][h] = add2(A1[k][h], r);
-                    if (GRAD) A2[k][h] = fma2(r, r, A2[k][h]);
                 }
             }
         }
@@ -272,8 +297,10 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
             unpack2(A2[k][1], b2, b3);
             const float S1 = (a0 + a1) + (a2 + a3);
             const float S2 = (b0 + b1) + (b2 + b3);
-            // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2)
-            acc_add(dl[k], positive ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
+            // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2).  Form 1 sums q = 1 - r: sum r = n - S1,
+            // and r - r^2 = q - q^2, so only the loss expressions swap
+            const bool small_side = ARVAE_PAIR_FORM == 1 ? !positive : positive;
+            acc_add(dl[k], small_side ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
             if (GRAD) acc_add(dg[k], positive ? S2 - S1 : S1 - S2);
         }
         return;
@@ -769,7 +796,7 @@ reg_tiles_kernel(TilesArgs a) {
     bool warp_has_rows = false;
     const float *Er = nullptr, *Xr = nullptr, *Ar = nullptr;
 #pragma unroll
-    for (int k = 0; k < kTileRI; ++k) { valid[k] = false; dl[k] = 0; dg[k] = 0; ds[k] = 0; R.e[k] = 1.0f; R.x[k] = 0.0f; R.a[k] = 0.0f; }
+    for (int k = 0; k < kTileRI; ++k) { valid[k] = false; dl[k] = 0; dg[k] = 0; ds[k] = 0; R.e[k] = 1.0f; R.f[k] = 1.0f; R.x[k] = 0.0f; R.a[k] = 0.0f; }
 
     // add this half's partial sums of row tile cur_rr to the row accumulators
     auto flush = [&]() {
@@ -841,6 +868,7 @@ reg_tiles_kernel(TilesArgs a) {
                 R.e[k] = valid[k] ? Er[pos] : 1.0f;
                 R.x[k] = valid[k] ? Xr[pos] : 0.0f;
                 R.a[k] = valid[k] ? Ar[pos] : 0.0f;
+                R.f[k] = exp2f(-(a.cabs * R.x[k]));  // as Es was built: 2^(cabs xs), with the opposite sign
             }
         }
 
