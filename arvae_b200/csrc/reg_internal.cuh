@@ -88,7 +88,7 @@ int run_extract_perm(const unsigned long long *keys, int64_t B, int32_t *perm, c
 int run_sign_matrix(const float *a, int64_t stride, int64_t B, int8_t *out, cudaStream_t st);
 
 // Layout of the small int array `flags` of a sorted-path call: [0, 32) whole-dim two-MUFU flags (unsegmented keys),
-// [32] plan error, [33] some element of some dim needs the two-MUFU form, [34] "last CTA" ticket of the plan kernel,
+// [32] plan error, [33] some element of some dim is an outlier or outside the shared-reciprocal range (|u| > 31), [34] "last CTA" ticket of the plan kernel,
 // [35, 67) per-dim non-finite latent bits (1: +-inf present, 2: NaN present), [67, 99) n_in per dim.
 constexpr int kFlagError = ARVAE_MAX_REG_DIMS;
 constexpr int kFlagAnyTwoMufu = ARVAE_MAX_REG_DIMS + 1;
@@ -110,6 +110,10 @@ struct KeySpec {
     RegDims dims;
 };
 constexpr float kMufu1MaxAbsU = 62.0f;
+// The pair kernel's build for the common case (reg_sorted.cu: ONLY1) shares one reciprocal between two pairs, 1 / (a b) with
+// a, b <= 1 + 2^(2 kSharedMaxAbsU): it runs only when every element of every dim is within this range (flag
+// kFlagAnyTwoMufu stays 0), the complete build otherwise.
+constexpr float kSharedMaxAbsU = 31.0f;
 constexpr unsigned long long kKeyIdxMask = 0x7FFFFFFFull;  // segmented keys: low 31 bits = sample index
 __host__ __device__ static inline bool key_is_outlier(unsigned long long k) { return (k >> 63) != 0; }
 __host__ __device__ static inline unsigned int key_sortable_attr(unsigned long long k) { return (unsigned int)(k >> 31); }

@@ -214,7 +214,7 @@ __device__ __forceinline__ void place_run_elem(const uint4 &e, int64_t pos, int6
     Es[base + pos] = key_is_outlier(key) ? 1.0f : exp2f(cabs * xs);
     perm[base + pos] = (int)(key & kKeyIdxMask);
     note_nonfinite(xs, flags, r);
-    if (key_is_outlier(key)) atomicOr(flags + kFlagAnyTwoMufu, 1);
+    if (key_is_outlier(key) || !(fabsf(cabs * xs) <= kSharedMaxAbsU)) atomicOr(flags + kFlagAnyTwoMufu, 1);
 }
 
 // One CTA per 256 consecutive elements of one run (and dim).  Their keys ascend, so inside any other run only the
@@ -719,6 +719,7 @@ int run_shard_step(ShardCtx &C, const ShardStep &S, cudaStream_t st) {
     a.B = B;
     a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
     a.shard = v;
+    a.dual = 1;
     const bool want_grad = S.grad_cols_out != nullptr || S.grad_z_out != nullptr;
 
     if (phases & 1) {

@@ -106,7 +106,7 @@ sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
         perm[o] = (int)idx;
         // unsegmented keys (triangle mode): one out-of-range element sends the whole dim to the two-MUFU form
         if (unsegmented && !(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + r, 1);
-        if (!(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + kFlagAnyTwoMufu, 1);
+        if (!(fabsf(u) <= kSharedMaxAbsU)) atomicOr(flags + kFlagAnyTwoMufu, 1);
         note_nonfinite(xs, flags, r);
         note_segment_boundary(kr, k, B, flags + kFlagNIn + r);
     } else {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
@@ -234,8 +234,23 @@ __device__ __forceinline__ f2_t rcp_newton2(f2_t x) {
 #define ARVAE_NR_MASK 0xC0C0
 #endif
 #endif
+// ARVAE_SHARE_MASK: which of the 8 (column group g, row k) quads (bit 4 g + k) of the pair group use the shared-reciprocal
+// form in the build for inner-range data (ONLY1); the others keep the plain form (with ARVAE_NR_MASK_SHARED).
+#ifndef ARVAE_ONLY1_SHARED
+#define ARVAE_ONLY1_SHARED 1
+#endif
+#ifndef ARVAE_SHARE_MASK
+#define ARVAE_SHARE_MASK 0xFF
+#endif
+#ifndef ARVAE_SHARE_FORM
+#define ARVAE_SHARE_FORM 2   // 1: both quotients of a quad (9 packed FP32 per four pairs), 2: their sums only (8; needs mask 0xFF)
+#endif
+static_assert(ARVAE_SHARE_FORM != 2 || ARVAE_SHARE_MASK == 0xFF, "the sums-only form needs every quad in the shared form");
+#ifndef ARVAE_NR_MASK_SHARED
+#define ARVAE_NR_MASK_SHARED 0x0000
+#endif
 #ifndef ARVAE_CONST_OUTER_UNROLL
-#define ARVAE_CONST_OUTER_UNROLL 1
+#define ARVAE_CONST_OUTER_UNROLL 8   // iterations of the 4 x 8 pair-group loop per branch: 1 3.90, 2 3.73, 4 3.62, 8 3.57, 16 3.61, 32 3.87 ms at C4
 #endif
 constexpr int kConstOuterUnroll = ARVAE_CONST_OUTER_UNROLL;
 
@@ -249,7 +264,7 @@ __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs)
 // PAIRS with the packed FP32 instructions: per two pairs FFMA2 (1 + E_j F_i), two MUFU.RCP (or, on 6 of 16 slots, the packed
 // Newton reciprocal on the FMA pipe), FADD2 (sum q), FFMA2 (sum q^2).  SASS of the loop: 118 instructions per 32 pairs
 // (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128): XU pipe 160 and FP32 pipe 156 clk per warp iteration.
-template <bool MUFU1, bool GRAD>
+template <bool MUFU1, bool GRAD, bool SHARED = false>
 __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,
                                            const float *__restrict__ sx, float cabs, bool positive,
                                            acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
@@ -269,12 +284,40 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
 #pragma unroll
                 for (int k = 0; k < kTileRI; ++k) {
                     const f2_t ri = ARVAE_PAIR_FORM == 1 ? pack2(R.f[k], R.f[k]) : pack2(R.e[k], R.e[k]);
+                    if (SHARED && ARVAE_PAIR_FORM == 1 && ((ARVAE_SHARE_MASK >> (g * 4 + k)) & 1)) {
+                        // two column pairs share their reciprocals: 1/a = b / (a b), 1/b = a / (a b) -- three FMUL2 and two
+                        // MUFU.RCP for four pairs instead of four MUFU.RCP.  a b <= (1 + 2^62)^2: the caller guarantees
+                        // |u| <= kSharedMaxAbsU for every element
+                        const f2_t sa = fma2(vv[0], ri, one), sb = fma2(vv[1], ri, one);
+                        float p0, p1;
+                        unpack2(mul2(sa, sb), p0, p1);
+                        const f2_t rp = pack2(rcp_approx(p0), rcp_approx(p1));
+                        if (ARVAE_SHARE_FORM == 2) {
+                            // sums of the quad without the two quotients: q_a + q_b = (a + b) / (a b) =: w, and
+                            // q_a^2 + q_b^2 = w^2 - 2 q_a q_b = w^2 - 2 / (a b): accumulate w, w^2 and 1 / (a b)
+                            const f2_t w = mul2(rp, add2(sa, sb));
+                            A1[k][0] = add2(A1[k][0], w);
+                            if (GRAD) {
+                                A2[k][0] = fma2(w, w, A2[k][0]);
+                                A2[k][1] = add2(A2[k][1], rp);
+                            }
+                            continue;
+                        }
+                        const f2_t qa = mul2(rp, sb), qb = mul2(rp, sa);
+                        A1[k][0] = add2(A1[k][0], qa);
+                        A1[k][1] = add2(A1[k][1], qb);
+                        if (GRAD) {
+                            A2[k][0] = fma2(qa, qa, A2[k][0]);
+                            A2[k][1] = fma2(qb, qb, A2[k][1]);
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         // form 0: E_i + E_j;  form 1: 1 + E_j F_i = (E_i + E_j) / E_i
                         const f2_t sum = ARVAE_PAIR_FORM == 1 ? fma2(vv[h], ri, one) : add2(ri, vv[h]);
                         f2_t rq;
-                        if ((ARVAE_NR_MASK >> (g * 8 + k * 2 + h)) & 1) {  // compile-time: a fixed subset of the 16 slots
+                        if (((SHARED ? ARVAE_NR_MASK_SHARED : ARVAE_NR_MASK) >> (g * 8 + k * 2 + h)) & 1) {  // compile-time: a fixed subset of the 16 slots
                             rq = rcp_newton2(sum);
                         } else {
                             float s0, s1;
@@ -296,7 +339,8 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
             unpack2(A2[k][0], b0, b1);
             unpack2(A2[k][1], b2, b3);
             const float S1 = (a0 + a1) + (a2 + a3);
-            const float S2 = (b0 + b1) + (b2 + b3);
+            const float S2 = (SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM == 2) ? fmaf(-2.0f, b2 + b3, b0 + b1)
+                                                                                       : (b0 + b1) + (b2 + b3);
             // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2).  Form 1 sums q = 1 - r: sum r = n - S1,
             // and r - r^2 = q - q^2, so only the loss expressions swap
             const bool small_side = ARVAE_PAIR_FORM == 1 ? !positive : positive;
@@ -478,19 +522,28 @@ __device__ __forceinline__ long long ceil_share(long long c, long long T, long l
     return (c * T + G - 1) / G;
 }
 
-// modelled cost (relative time) of one warp's 128 x 256 tile, by class and tanh form; the one-MUFU constant-sign
-// tile (packed loop) is the unit = 8
+// Modelled cost (relative time) of one warp's 128 x 256 tile by class and tanh form, in units where the one-MUFU
+// constant-sign tile of the build that will run is 8.  The build is known when the plan is made (flag kFlagAnyTwoMufu):
+// the common-case build (ONLY1: shared-reciprocal constant-sign loop, 3.57 ms at C4) or the complete one (plain loop,
+// 4.53 ms).  The warps of a half wait for each other at every grant, so a slow tile costs its half more than its share
+// of the instructions: the constants are fitted, not counted -- pair kernel at B = 65 536 on dSprites-shaped labels
+// (up to 33 % ties), ms, by (general, tie): (21, 12) 4.82, (30, 17) 4.32, (38, 21) 4.04, (42, 23) 3.78, (50, 27) 3.76,
+// (50, 31) 3.87, (50, 36) 4.02; C4 (2 % general units, no ties) does not react (3.57 throughout).
 #ifndef ARVAE_COST_GENERAL1
-#define ARVAE_COST_GENERAL1 21
+#define ARVAE_COST_GENERAL1 46
 #endif
 #ifndef ARVAE_COST_TIE1
-#define ARVAE_COST_TIE1 12
+#define ARVAE_COST_TIE1 25
 #endif
-__device__ __forceinline__ int class_cost(int cls, bool mufu1) {
+__device__ __forceinline__ int class_cost(int cls, bool mufu1, bool shared_build) {
     // general, pos, neg, tie
-    constexpr unsigned int k1 = (unsigned int)ARVAE_COST_GENERAL1 | (8u << 8) | (8u << 16) | ((unsigned int)ARVAE_COST_TIE1 << 24);
-    return mufu1 ? ((k1 >> (8 * cls)) & 0xFF)
-                 : ((0x1212'1216u >> (8 * cls)) & 0xFF);  // two-MUFU forms: 22, 18, 18, 18
+    constexpr unsigned int ks = (unsigned int)ARVAE_COST_GENERAL1 | (8u << 8) | (8u << 16) | ((unsigned int)ARVAE_COST_TIE1 << 24);
+    // complete build: the same loops against a constant-sign loop that takes 4.53 / 3.57 as long; two-MUFU forms
+    // (EX2 + RCP per pair: XU-bound at 512 clk per 32 pairs against ~209): general 26, constant-sign 22, tie 23
+    constexpr unsigned int k1 = (unsigned int)(ARVAE_COST_GENERAL1 * 357 / 453) | (8u << 8) | (8u << 16) |
+                                ((unsigned int)(ARVAE_COST_TIE1 * 357 / 453) << 24);
+    if (shared_build) return (ks >> (8 * cls)) & 0xFF;
+    return mufu1 ? ((k1 >> (8 * cls)) & 0xFF) : ((0x1716'161Au >> (8 * cls)) & 0xFF);
 }
 
 // One CTA per row tile rr: class byte and cost of each of its S units (in visiting order), and the
@@ -517,6 +570,7 @@ plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost, int clear_acc, un
     const float *Ar = a.As + (int64_t)r * a.Bpad;
     const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
     const bool dim_mufu1 = a.flags[r] == 0;
+    const bool shared_build = a.dual && a.flags[kFlagAnyTwoMufu] == 0;  // which build of the pair kernel will work
     const int64_t nin = a.n_in[r];
     constexpr int kWarpRows = kTileRows / (kTileThreads / 32);
     if (threadIdx.x < kTileThreads / 32) {
@@ -547,7 +601,7 @@ plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost, int clear_acc, un
             const bool mufu1 = dim_mufu1 && win[w] && col_in;
             word |= (unsigned int)cls << (2 * w);
             word |= (mufu1 ? 0u : 1u) << (16 + w);
-            if (whas[w]) cost += class_cost(cls, mufu1);
+            if (whas[w]) cost += class_cost(cls, mufu1, shared_build);
         }
         a.cls8[rr * a.S + sp] = word;
         a.cost8[rr * a.S + sp] = (unsigned short)cost;
@@ -700,18 +754,18 @@ __device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, 
     __syncthreads();
 }
 
-template <bool MUFU1, bool GRAD, bool SIGNS>
+template <bool MUFU1, bool GRAD, bool SIGNS, bool SHARED = false>
 __device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const float *se,
                                                const float *sx, const float *sa, float cabs,
                                                acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], int (&ds)[kTileRI]) {
     if (cls == kClassPos) {
-        loop_const<MUFU1, GRAD>(R, se, sx, cabs, true, dl, dg);
+        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, true, dl, dg);
         if (SIGNS) {
 #pragma unroll
             for (int k = 0; k < kTileRI; ++k) ds[k] += kSubCols;
         }
     } else if (cls == kClassNeg) {
-        loop_const<MUFU1, GRAD>(R, se, sx, cabs, false, dl, dg);
+        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, false, dl, dg);
         if (SIGNS) {
 #pragma unroll
             for (int k = 0; k < kTileRI; ++k) ds[k] -= kSubCols;
@@ -887,7 +941,7 @@ reg_tiles_kernel(TilesArgs a) {
                 const unsigned int word = a.cls8[rr * a.S + sp + w];
                 const int cls = (word >> (2 * warp)) & 3;        // planned class of this warp's tile
                 const bool mufu1 = ONLY1 || ((word >> (16 + warp)) & 1u) == 0u;  // planned tanh form
-                if (mufu1) sweep_subchunk<true, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
+                if (mufu1) sweep_subchunk<true, GRAD, SIGNS, ONLY1 && ARVAE_ONLY1_SHARED>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
                 else sweep_subchunk<false, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
             }
         }
@@ -1008,14 +1062,14 @@ static int tiles_ctas_per_sm() {
     return v;
 }
 
+// a.dual (set by the caller BEFORE the plan is made: the cost model depends on it): 0 = the complete build only (parity
+// instrumentation), 1 = both builds, the device flag decides which one works
 static void launch_tiles(TilesArgs a, int n_cta, bool want_grad, bool want_signs, cudaStream_t st) {
     const dim3 grid((unsigned)n_cta), block(kDuoThreads);
-    if (want_signs) {  // parity instrumentation: the complete build only
-        a.dual = 0;
+    if (want_signs) {
         launch_kernel(reg_tiles_kernel<true, true, false>, grid, block, kDuoStageBytes, st, true, a);
         return;
     }
-    a.dual = 1;  // both builds; the device flag decides which one works
     if (want_grad) {
         launch_kernel(reg_tiles_kernel<true, false, true>, grid, block, kDuoStageBytes, st, true, a);
         launch_kernel(reg_tiles_kernel<true, false, false>, grid, block, kDuoStageBytes, st, true, a);
@@ -1187,6 +1241,7 @@ int run_reg_sorted(const RegProblem &P, const SortedLayout &L, char *ws, cudaStr
     a.lossp = reinterpret_cast<acc_t *>(ws + L.off_lossp);
     a.dbg_times = getenv("ARVAE_DEBUG_TIMES") ? reinterpret_cast<unsigned long long *>(ws + L.off_dbg) : nullptr;
     a.colpart = nullptr; a.Pinv = 0; a.B = P.B;
+    a.dual = want_signs ? 0 : 1;
     if (triangle) return run_reg_tri_tail(P, L, a, perm, combo_cost, ws, st);
 
     if (n_rows > 0) {

@@ -42,14 +42,22 @@ MUFU_LANES_PER_CLK_SM = 16.0     # sm_100 MUFU issue rate; confirmed by bench_to
 # MUFU per evaluated pair: 2 (EX2 + RCP on the latent difference, SURVEY App. B's cheapest admissible
 # dense form) on the dense path; 1 (RCP only, E_j/(E_i+E_j) with E = 2^u precomputed per element) where
 # the attribute-sorted path's range guard holds.  Measured per run via arvae_b200.mufu_per_pair().
-# The one-MUFU constant-sign loop (reg_sorted.cu: loop_const) works on column pairs with packed FP32 instructions
-# (q = 1 / (1 + E_j F_i): FFMA2, reciprocal, FADD2, FFMA2); 6 of the 16 (column group, row, column pair) slots of a 4 x 8 pair
-# group (ARVAE_NR_MASK) take their reciprocals from a packed Newton iteration on the FMA pipe instead of MUFU.RCP.  SASS of
-# that loop (cuobjdump): 118 instructions per 32 pairs -- 20 MUFU.RCP, 62 FFMA2, 16 FADD2 (two FP32 operations each),
-# 12 IADD3, 2 LDS.128, 6 others.  Used for the roofs of the ACTUAL mix.
-NR_SLOTS_OF_16 = 6
-CONST_LOOP_INSTR_PER_PAIR = 118.0 / 32.0
-CONST_LOOP_FP32_OPS_PER_PAIR = (62 + 16) * 2 / 32.0
+# The one-MUFU constant-sign loop (reg_sorted.cu: loop_const) works on column pairs with packed FP32 instructions, in two
+# builds of the pair kernel (cuobjdump -sass of the loops):
+#  * common case, every |2 f log2(e) z| <= 31 (kSharedMaxAbsU): two column pairs share their reciprocals through
+#    1 / (a b) and only the sums q_a + q_b and q_a^2 + q_b^2 are formed -- 674 instructions per 256 pairs: 128 MUFU.RCP,
+#    192 FFMA2, 128 FMUL2, 192 FADD2 (two FP32 operations each), 16 LDS.128, 18 others;
+#  * complete build (outliers or latents beyond that range present): q = 1 / (1 + E_j F_i) per pair, 6 of the 16 slots of a
+#    4 x 8 pair group take their reciprocals from a packed Newton iteration on the FMA pipe -- 118 instructions per
+#    32 pairs: 20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128, 6 others.
+# Used for the roofs of the ACTUAL mix.
+SHARED_MAX_ABS_U = 31.0
+SHARED_LOOP = {"mufu_per_inlier_pair": 128.0 / 256.0, "instr_per_pair": 674.0 / 256.0, "fp32_ops_per_pair": (192 + 128 + 192) * 2 / 256.0,
+               "sass": "674 instructions per 256 pairs (128 MUFU.RCP, 192 FFMA2, 128 FMUL2, 192 FADD2, 16 LDS.128)",
+               "what": "shared-reciprocal build (every |u| <= 31): one MUFU.RCP per two pairs"}
+PLAIN_LOOP = {"mufu_per_inlier_pair": 20.0 / 32.0, "instr_per_pair": 118.0 / 32.0, "fp32_ops_per_pair": (62 + 16) * 2 / 32.0,
+              "sass": "118 instructions per 32 pairs (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3)",
+              "what": "complete build: 6 of 16 slots per pair group take packed Newton reciprocals on the FMA pipe"}
 ISSUE_LANES_PER_CLK_SM = 128.0   # 4 schedulers x 32 lanes
 FP32_LANES_PER_CLK_SM = 128.0    # FMA pipe (FFMA2 / FADD2 / FMUL2 measured at 123 FP32 operations/clk/SM, profiles/r2_pipe_rates.json)
 ALGO_BYTES_PER_ROWCOL = 4        # float32 per latent / label / gradient element
@@ -562,11 +570,15 @@ def main():
     per_dim = arvae_b200.mufu_per_pair(case["z"].to(dev), case["labels"].to(dev), dims, gamma, delta, algo=args.algo)
     MUFU_PER_PAIR = sum(per_dim) / len(per_dim)
     mufu_peak = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / MUFU_PER_PAIR  # Gpairs/s per GPU, one MUFU per inlier pair
-    # the kernel's ACTUAL mix: NR_SLOTS_OF_16 of every 16 inlier slots take the reciprocal on the FMA pipe
-    mufu_mix = MUFU_PER_PAIR - (NR_SLOTS_OF_16 / 16.0) * (2.0 - MUFU_PER_PAIR)  # outlier pairs keep both MUFU
+    # the kernel's ACTUAL mix: which build of the pair kernel ran (reg_internal.cuh: kSharedMaxAbsU) and its loop's SASS;
+    # an inlier pair costs the loop's MUFU share, a pair with an outlier (2 - MUFU_PER_PAIR of them per pair) keeps both MUFU
+    zreg = case["z"].to(dev)[:, list(dims)]
+    u_max = float((2.0 * abs(delta) * 1.4426950408889634 * zreg.abs()).max().item()) if zreg.numel() else 0.0
+    loop = SHARED_LOOP if (MUFU_PER_PAIR == 1.0 and u_max <= SHARED_MAX_ABS_U) else PLAIN_LOOP
+    mufu_mix = MUFU_PER_PAIR - (1.0 - loop["mufu_per_inlier_pair"]) * (2.0 - MUFU_PER_PAIR)
     mufu_peak_mix = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / mufu_mix
-    issue_peak_mix = ISSUE_LANES_PER_CLK_SM * sm_count * f_ghz / CONST_LOOP_INSTR_PER_PAIR
-    fma_peak_mix = FP32_LANES_PER_CLK_SM * sm_count * f_ghz / CONST_LOOP_FP32_OPS_PER_PAIR
+    issue_peak_mix = ISSUE_LANES_PER_CLK_SM * sm_count * f_ghz / loop["instr_per_pair"]
+    fma_peak_mix = FP32_LANES_PER_CLK_SM * sm_count * f_ghz / loop["fp32_ops_per_pair"]
     peak_mix = min(mufu_peak_mix, issue_peak_mix, fma_peak_mix)
     mufu_peak_2 = MUFU_LANES_PER_CLK_SM * sm_count * f_ghz / 2.0
     k_ms = (ksum.value / kn.value) if kn.value else ms_step
@@ -579,12 +591,11 @@ def main():
     roofline = {
         "bound": "mufu", "achieved": achieved, "peak": peak_mix, "unit": "Gpairs/s", "frac": achieved / peak_mix,
         "traffic": traffic,
-        "peak_of_actual_mix": {"mufu_per_pair": mufu_mix, "mufu_roof": mufu_peak_mix, "instr_per_pair": CONST_LOOP_INSTR_PER_PAIR,
-                               "issue_roof": issue_peak_mix, "fp32_ops_per_pair": CONST_LOOP_FP32_OPS_PER_PAIR,
-                               "fma_pipe_roof": fma_peak_mix,
-                               "note": f"{NR_SLOTS_OF_16} of 16 slots per pair group take packed Newton reciprocals on the FMA pipe "
-                                       "(reg_sorted.cu ARVAE_NR_MASK); SASS of the constant-sign loop: 118 instructions per 32 pairs "
-                                       "(20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3); `peak` = the lowest of the three roofs of that mix"},
+        "peak_of_actual_mix": {"mufu_per_pair": mufu_mix, "mufu_roof": mufu_peak_mix, "instr_per_pair": loop["instr_per_pair"],
+                               "issue_roof": issue_peak_mix, "fp32_ops_per_pair": loop["fp32_ops_per_pair"],
+                               "fma_pipe_roof": fma_peak_mix, "max_abs_u": u_max,
+                               "note": f"{loop['what']} (reg_sorted.cu: loop_const); SASS of the constant-sign loop: {loop['sass']}; "
+                                       "`peak` = the lowest of the three roofs of that mix"},
         "frac_of_1mufu_roof": achieved / mufu_peak, "peak_1mufu": mufu_peak,
         "traffic_source": "profiles/r1_final_ncu_full_summary.csv (ncu --set full, reg_tiles_kernel<true>)" if traffic else None,
         "peak_source": f"{MUFU_LANES_PER_CLK_SM:.0f} MUFU lanes/clk/SM x {sm_count} SMs x {f_ghz:.3f} GHz (sm_max_mhz, "

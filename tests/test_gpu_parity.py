@@ -597,6 +597,29 @@ def test_outliers_of_the_one_mufu_form_get_their_own_segment(ab, oracle_mod):
     assert set(ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 2), 1.0, 10.0, algo=3)) == {2.0}
 
 
+@pytest.mark.parametrize("zmax", [10.7, 10.8, 21.0])
+def test_shared_reciprocal_build_and_its_range_boundary(ab, oracle_mod, zmax):
+    """The pair kernel's build for the common case shares one reciprocal between two pairs, 1 / (a b) with
+    a, b <= 1 + 2^62, which is valid while |2 f log2(e) z| <= 31 for EVERY element (|z| <= 10.74 at delta = 1); one element
+    beyond that (still an inlier of the one-MUFU form, |u| <= 62) sends the call to the complete build.  Both sides of
+    the boundary, and widely spread latents inside it (products up to 2^124), match the float64 oracle."""
+    B = 8192 + 512
+    g = torch.Generator().manual_seed(33)
+    z = torch.randn(B, 2, generator=g) * 3.0
+    z.clamp_(-10.7, 10.7)
+    z[7, 0] = zmax
+    z[11, 1] = -zmax
+    z[13, 0] = -10.7        # with z[7, 0]: 1 + 2^(u_j - u_i) up to 1 + 2^61.7 inside the shared form
+    labels = torch.stack([torch.randn(B, generator=g), torch.randint(0, 5, (B,), generator=g).float()], dim=1)
+    assert ab.mufu_per_pair(z.cuda(), labels.cuda(), (0, 1), 1.0, 1.0) == (1.0, 1.0)  # nobody is an outlier
+    ref_loss, ref_grad = oracle_mod.compute_reg_loss_multi(z.numpy(), labels.numpy(), (0, 1), 1.0, 1.0, f64=True)
+    zc = z.cuda().requires_grad_(True)
+    loss = ab.reg_loss_fused(zc, labels.cuda(), (0, 1), 1.0, 1.0, algo=2)
+    loss.backward()
+    assert_loss_close(loss.item(), ref_loss)
+    assert_grad_close(zc.grad.cpu().numpy(), ref_grad)
+
+
 @pytest.mark.parametrize("algo", [2, 3])
 @pytest.mark.parametrize("case", ["delta10", "all_outliers", "nan_latent", "boundary_in_tile"])
 def test_outlier_segment_against_f64_oracle(ab, oracle_mod, algo, case):
