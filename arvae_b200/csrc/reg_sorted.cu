@@ -177,6 +177,7 @@ __device__ __forceinline__ void acc_add(acc_t &acc, float v) {
 struct RowRegs {
     float e[kTileRI];  // 2^u_i          (1-MUFU form)
     float f[kTileRI];  // 2^-u_i         (1-MUFU form of the constant-sign loop, ARVAE_PAIR_FORM 1)
+    float f2[kTileRI]; // 2^-2u_i        (shared-reciprocal loop on staged column-pair sums and products, ARVAE_SHARE_FORM 3)
     float x[kTileRI];  // sgn(f) x_i     (2-MUFU form, exact tie signs)
     float a[kTileRI];  // attribute
 };
@@ -243,9 +244,16 @@ __device__ __forceinline__ f2_t rcp_newton2(f2_t x) {
 #define ARVAE_SHARE_MASK 0xFF
 #endif
 #ifndef ARVAE_SHARE_FORM
-#define ARVAE_SHARE_FORM 2   // 1: both quotients of a quad (9 packed FP32 per four pairs), 2: their sums only (8; needs mask 0xFF)
+#define ARVAE_SHARE_FORM 3   // 1: both quotients of a quad (9 packed FP32 per four pairs), 2: their sums only (8; needs mask 0xFF),
+                             // 3: the sums from staged column-pair sums and products (6; needs mask 0xFF)
 #endif
-static_assert(ARVAE_SHARE_FORM != 2 || ARVAE_SHARE_MASK == 0xFF, "the sums-only form needs every quad in the shared form");
+static_assert(ARVAE_SHARE_FORM < 2 || ARVAE_SHARE_MASK == 0xFF, "the sums-only forms need every quad in the shared form");
+#ifndef ARVAE_NR_MASK_TP
+#define ARVAE_NR_MASK_TP 0x10   // form 3: which of the 8 (column group g, row k) quads (bit 4 g + k) take the packed Newton reciprocal.
+                                // Pair kernel at C4, ms: none 3.51; one quad 3.21-3.25 (0x10 3.214, 0x20 3.218, 0x02 3.225, 0x01 3.229,
+                                // 0x40 3.231, 0x04 3.252; 0x08 3.54, 0x80 3.53); two quads 3.31-3.39; form 2 (no staged sums) 3.57
+#endif
+constexpr bool kStageTP = ARVAE_ONLY1_SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM == 3;
 #ifndef ARVAE_NR_MASK_SHARED
 #define ARVAE_NR_MASK_SHARED 0x0000
 #endif
@@ -267,7 +275,7 @@ __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs)
 template <bool MUFU1, bool GRAD, bool SHARED = false>
 __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,
                                            const float *__restrict__ sx, float cabs, bool positive,
-                                           acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
+                                           acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], const float *__restrict__ stp = nullptr) {
     if (MUFU1) {
         f2_t A1[kTileRI][2], A2[kTileRI][2];
 #pragma unroll
@@ -279,6 +287,34 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
         for (int q = 0; q < kSubCols; q += 8) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
+                if (SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM == 3) {
+                    // The quad (columns j, j+2 and j+1, j+3 of a group of four, row i) from the STAGED column-pair sums
+                    // T = E_a + E_b and products P = E_a E_b:  a + b - 1 = 1 + T F_i,  a b = (a + b - 1) + P F_i^2,
+                    // w = q_a + q_b = (a + b) / (a b) -- three FFMA2 where the per-pair form needs five packed operations.
+                    const float4 tp = *reinterpret_cast<const float4 *>(stp + q + 4 * g);
+                    const f2_t T = pack2(tp.x, tp.y), P = pack2(tp.z, tp.w);
+#pragma unroll
+                    for (int k = 0; k < kTileRI; ++k) {
+                        const f2_t fk = pack2(R.f[k], R.f[k]), fk2 = pack2(R.f2[k], R.f2[k]);
+                        const f2_t tm1 = fma2(T, fk, one);
+                        const f2_t p = fma2(P, fk2, tm1);
+                        f2_t rp;
+                        if ((ARVAE_NR_MASK_TP >> (g * 4 + k)) & 1) {
+                            rp = rcp_newton2(p);
+                        } else {
+                            float p0, p1;
+                            unpack2(p, p0, p1);
+                            rp = pack2(rcp_approx(p0), rcp_approx(p1));
+                        }
+                        const f2_t w = fma2(rp, tm1, rp);
+                        A1[k][0] = add2(A1[k][0], w);
+                        if (GRAD) {
+                            A2[k][0] = fma2(w, w, A2[k][0]);
+                            A2[k][1] = add2(A2[k][1], rp);
+                        }
+                    }
+                    continue;
+                }
                 const float4 vj = *reinterpret_cast<const float4 *>(se + q + 4 * g);
                 const f2_t vv[2] = {pack2(vj.x, vj.y), pack2(vj.z, vj.w)};
 #pragma unroll
@@ -339,7 +375,7 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
             unpack2(A2[k][0], b0, b1);
             unpack2(A2[k][1], b2, b3);
             const float S1 = (a0 + a1) + (a2 + a3);
-            const float S2 = (SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM == 2) ? fmaf(-2.0f, b2 + b3, b0 + b1)
+            const float S2 = (SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM >= 2) ? fmaf(-2.0f, b2 + b3, b0 + b1)
                                                                                        : (b0 + b1) + (b2 + b3);
             // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2).  Form 1 sums q = 1 - r: sum r = n - S1,
             // and r - r^2 = q - q^2, so only the loss expressions swap
@@ -757,15 +793,16 @@ __device__ __forceinline__ void find_unit(const TilesArgs &a, long long target, 
 template <bool MUFU1, bool GRAD, bool SIGNS, bool SHARED = false>
 __device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const float *se,
                                                const float *sx, const float *sa, float cabs,
-                                               acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], int (&ds)[kTileRI]) {
+                                               acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], int (&ds)[kTileRI],
+                                               const float *stp = nullptr) {
     if (cls == kClassPos) {
-        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, true, dl, dg);
+        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, true, dl, dg, stp);
         if (SIGNS) {
 #pragma unroll
             for (int k = 0; k < kTileRI; ++k) ds[k] += kSubCols;
         }
     } else if (cls == kClassNeg) {
-        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, false, dl, dg);
+        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, false, dl, dg, stp);
         if (SIGNS) {
 #pragma unroll
             for (int k = 0; k < kTileRI; ++k) ds[k] -= kSubCols;
@@ -789,7 +826,8 @@ __device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const 
 // of GPUs.
 constexpr int kDuoThreads = 2 * kTileThreads;
 constexpr int kStageSubs = kStageCols / kSubCols;
-constexpr int kDuoStageBytes = 2 * 3 * kStageCols * (int)sizeof(float);  // 48 KiB
+constexpr int kStageArrays = 4;  // 2^u, sgn(f) x, attribute; column-pair sums and products of 2^u (shared-reciprocal build)
+constexpr int kDuoStageBytes = 2 * kStageArrays * kStageCols * (int)sizeof(float);  // 64 KiB
 
 __device__ __forceinline__ void half_barrier(int half) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(kTileThreads) : "memory");
@@ -810,7 +848,7 @@ __device__ void shard_pair_kernel_tail(const TilesArgs &a, acc_t *sh);  // reg_s
 template <bool GRAD, bool SIGNS, bool ONLY1>
 __global__ void __launch_bounds__(kDuoThreads, 1)
 reg_tiles_kernel(TilesArgs a) {
-    extern __shared__ __align__(16) float stage[];  // [2 halves][3 arrays][kStageCols] = kDuoStageBytes (dynamic)
+    extern __shared__ __align__(16) float stage[];  // [2 halves][kStageArrays][kStageCols] = kDuoStageBytes (dynamic)
     __shared__ acc_t sred[2][kDuoThreads / 32];
     __shared__ int s_rng[4];
     __shared__ int s_scan[kDuoThreads];
@@ -837,8 +875,8 @@ reg_tiles_kernel(TilesArgs a) {
     const int tid = threadIdx.x % kTileThreads;
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int kWarpRows = kTileRows / (kTileThreads / 32);
-    float *hse = stage + (half * 3 + 0) * kStageCols, *hsx = stage + (half * 3 + 1) * kStageCols,
-          *hsa = stage + (half * 3 + 2) * kStageCols;
+    float *hse = stage + (half * kStageArrays + 0) * kStageCols, *hsx = stage + (half * kStageArrays + 1) * kStageCols,
+          *hsa = stage + (half * kStageArrays + 2) * kStageCols, *hstp = stage + (half * kStageArrays + 3) * kStageCols;
 
     int64_t cursor = half == 0 ? 0 : N;  // next unit from the front / one past the next unit from the back
     int64_t cur_rr = -1;
@@ -850,7 +888,7 @@ reg_tiles_kernel(TilesArgs a) {
     bool warp_has_rows = false;
     const float *Er = nullptr, *Xr = nullptr, *Ar = nullptr;
 #pragma unroll
-    for (int k = 0; k < kTileRI; ++k) { valid[k] = false; dl[k] = 0; dg[k] = 0; ds[k] = 0; R.e[k] = 1.0f; R.f[k] = 1.0f; R.x[k] = 0.0f; R.a[k] = 0.0f; }
+    for (int k = 0; k < kTileRI; ++k) { valid[k] = false; dl[k] = 0; dg[k] = 0; ds[k] = 0; R.e[k] = 1.0f; R.f[k] = 1.0f; R.f2[k] = 1.0f; R.x[k] = 0.0f; R.a[k] = 0.0f; }
 
     // add this half's partial sums of row tile cur_rr to the row accumulators
     auto flush = [&]() {
@@ -923,6 +961,7 @@ reg_tiles_kernel(TilesArgs a) {
                 R.x[k] = valid[k] ? Xr[pos] : 0.0f;
                 R.a[k] = valid[k] ? Ar[pos] : 0.0f;
                 R.f[k] = exp2f(-(a.cabs * R.x[k]));  // as Es was built: 2^(cabs xs), with the opposite sign
+                R.f2[k] = R.f[k] * R.f[k];
             }
         }
 
@@ -930,7 +969,10 @@ reg_tiles_kernel(TilesArgs a) {
         for (int q = tid * 4; q < nsub * kSubCols; q += kTileThreads * 4) {
             const int w = q / kSubCols;
             const int64_t col = (((int64_t)(sp + w) * a.P) % a.S) * kSubCols + (q - w * kSubCols);
-            *reinterpret_cast<float4 *>(hse + q) = *reinterpret_cast<const float4 *>(Er + col);
+            const float4 e4 = *reinterpret_cast<const float4 *>(Er + col);
+            *reinterpret_cast<float4 *>(hse + q) = e4;
+            if (ONLY1 && kStageTP)  // per group of four columns: sums and products of the column pairs (j, j+2), (j+1, j+3)
+                *reinterpret_cast<float4 *>(hstp + q) = make_float4(e4.x + e4.z, e4.y + e4.w, e4.x * e4.z, e4.y * e4.w);
             *reinterpret_cast<float4 *>(hsx + q) = *reinterpret_cast<const float4 *>(Xr + col);
             *reinterpret_cast<float4 *>(hsa + q) = *reinterpret_cast<const float4 *>(Ar + col);
         }
@@ -941,7 +983,7 @@ reg_tiles_kernel(TilesArgs a) {
                 const unsigned int word = a.cls8[rr * a.S + sp + w];
                 const int cls = (word >> (2 * warp)) & 3;        // planned class of this warp's tile
                 const bool mufu1 = ONLY1 || ((word >> (16 + warp)) & 1u) == 0u;  // planned tanh form
-                if (mufu1) sweep_subchunk<true, GRAD, SIGNS, ONLY1 && ARVAE_ONLY1_SHARED>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
+                if (mufu1) sweep_subchunk<true, GRAD, SIGNS, ONLY1 && ARVAE_ONLY1_SHARED>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds, hstp + sub);
                 else sweep_subchunk<false, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
             }
         }

@@ -44,17 +44,20 @@ MUFU_LANES_PER_CLK_SM = 16.0     # sm_100 MUFU issue rate; confirmed by bench_to
 # the attribute-sorted path's range guard holds.  Measured per run via arvae_b200.mufu_per_pair().
 # The one-MUFU constant-sign loop (reg_sorted.cu: loop_const) works on column pairs with packed FP32 instructions, in two
 # builds of the pair kernel (cuobjdump -sass of the loops):
-#  * common case, every |2 f log2(e) z| <= 31 (kSharedMaxAbsU): two column pairs share their reciprocals through
-#    1 / (a b) and only the sums q_a + q_b and q_a^2 + q_b^2 are formed -- 674 instructions per 256 pairs: 128 MUFU.RCP,
-#    192 FFMA2, 128 FMUL2, 192 FADD2 (two FP32 operations each), 16 LDS.128, 18 others;
+#  * common case, every |2 f log2(e) z| <= 31 (kSharedMaxAbsU): two column pairs share one reciprocal, 1 / (a b), and only
+#    the sums q_a + q_b and q_a^2 + q_b^2 are formed, from column-pair sums and products staged in shared memory; one of
+#    the eight quads of a 4 x 8 pair group takes its reciprocals from a packed Newton iteration on the FMA pipe -- 580
+#    instructions per 256 pairs: 112 MUFU.RCP, 296 FFMA2, 128 FADD2 (two FP32 operations each), 17 IADD3, 16 LDS.128,
+#    11 others;
 #  * complete build (outliers or latents beyond that range present): q = 1 / (1 + E_j F_i) per pair, 6 of the 16 slots of a
 #    4 x 8 pair group take their reciprocals from a packed Newton iteration on the FMA pipe -- 118 instructions per
 #    32 pairs: 20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128, 6 others.
 # Used for the roofs of the ACTUAL mix.
 SHARED_MAX_ABS_U = 31.0
-SHARED_LOOP = {"mufu_per_inlier_pair": 128.0 / 256.0, "instr_per_pair": 674.0 / 256.0, "fp32_ops_per_pair": (192 + 128 + 192) * 2 / 256.0,
-               "sass": "674 instructions per 256 pairs (128 MUFU.RCP, 192 FFMA2, 128 FMUL2, 192 FADD2, 16 LDS.128)",
-               "what": "shared-reciprocal build (every |u| <= 31): one MUFU.RCP per two pairs"}
+SHARED_LOOP = {"mufu_per_inlier_pair": 112.0 / 256.0, "instr_per_pair": 580.0 / 256.0, "fp32_ops_per_pair": (296 + 128) * 2 / 256.0,
+               "sass": "580 instructions per 256 pairs (112 MUFU.RCP, 296 FFMA2, 128 FADD2, 17 IADD3, 16 LDS.128)",
+               "what": "shared-reciprocal build (every |u| <= 31): one reciprocal per two pairs from staged column-pair sums and "
+                       "products, 1 of 8 quads on packed Newton reciprocals"}
 PLAIN_LOOP = {"mufu_per_inlier_pair": 20.0 / 32.0, "instr_per_pair": 118.0 / 32.0, "fp32_ops_per_pair": (62 + 16) * 2 / 32.0,
               "sass": "118 instructions per 32 pairs (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3)",
               "what": "complete build: 6 of 16 slots per pair group take packed Newton reciprocals on the FMA pipe"}
