@@ -65,7 +65,7 @@ ISSUE_LANES_PER_CLK_SM = 128.0   # 4 schedulers x 32 lanes
 FP32_LANES_PER_CLK_SM = 128.0    # FMA pipe (FFMA2 / FADD2 / FMUL2 measured at 123 FP32 operations/clk/SM, profiles/r2_pipe_rates.json)
 ALGO_BYTES_PER_ROWCOL = 4        # float32 per latent / label / gradient element
 # (B, R, n_gpus, algo) -> dram__bytes_read.sum + dram__bytes_write.sum of one pair-kernel launch (ncu, profiles/)
-NCU_DRAM_BYTES_PER_LAUNCH = {(65536, 6, 1, 0): 5261056 + 0}
+NCU_DRAM_BYTES_PER_LAUNCH = {(65536, 6, 1, 0): 8412928 + 0}
 
 
 def load_peaks():
@@ -600,7 +600,7 @@ def main():
                                "note": f"{loop['what']} (reg_sorted.cu: loop_const); SASS of the constant-sign loop: {loop['sass']}; "
                                        "`peak` = the lowest of the three roofs of that mix"},
         "frac_of_1mufu_roof": achieved / mufu_peak, "peak_1mufu": mufu_peak,
-        "traffic_source": "profiles/r1_final_ncu_full_summary.csv (ncu --set full, reg_tiles_kernel<true>)" if traffic else None,
+        "traffic_source": "profiles/r2c_pair_ncu_full_summary.csv (ncu --set full, reg_tiles_kernel<1, 0, 1>)" if traffic else None,
         "peak_source": f"{MUFU_LANES_PER_CLK_SM:.0f} MUFU lanes/clk/SM x {sm_count} SMs x {f_ghz:.3f} GHz (sm_max_mhz, "
                        f"MEASURED_PEAKS.json {peaks_src}) / {mufu_mix:.4f} MUFU per evaluated pair (this run's "
                        "algorithm and instruction mix; every one of the B^2 R ordered pairs is evaluated); "
