@@ -176,89 +176,57 @@ __device__ __forceinline__ void acc_add(acc_t &acc, float v) {
 // Per-thread row operands of one row tile.
 struct RowRegs {
     float e[kTileRI];  // 2^u_i          (1-MUFU form)
-    float f[kTileRI];  // 2^-u_i         (1-MUFU form of the constant-sign loop, ARVAE_PAIR_FORM 1)
-    float f2[kTileRI]; // 2^-2u_i        (shared-reciprocal loop on staged column-pair sums and products, ARVAE_SHARE_FORM 3)
+    float f[kTileRI];  // 2^-u_i         (one-MUFU constant-sign loops: q = 1 / (1 + E_j F_i))
+    float f2[kTileRI]; // 2^-2u_i        (shared-reciprocal loop on staged column-pair sums and products)
     float x[kTileRI];  // sgn(f) x_i     (2-MUFU form, exact tie signs)
     float a[kTileRI];  // attribute
 };
 
-// Reciprocal on the FMA pipe for a fixed share of the pairs of the constant-sign loop, so that the XU pipe (MUFU.RCP,
+// Reciprocal on the FMA pipe for a fixed share of the pairs of the constant-sign loops, so that the XU pipe (MUFU.RCP,
 // 16 lanes/clk/SM) and the FP32 pipe are both kept busy: magic-constant seed (relative error < 0.051), one quadratic
 // Newton step (-> 2.6e-3) and one cubic step y (1 + e + e^2) (-> 1.8e-8; measured over 3e6 arguments in [1, 2^124]:
-// 1.28 * 2^-24, within an ulp like MUFU.RCP itself) -- five FFMA2 and two IADD per TWO reciprocals.  ARVAE_NR_OPS 6
-// keeps round 2's three quadratic steps (4.6e-11 before rounding; 4.73 instead of 4.53 ms at C4).  Valid for normal
+// 1.28 * 2^-24, within an ulp like MUFU.RCP itself; tests/test_pair_arithmetic.py) -- five FFMA2 and two IADD per TWO
+// reciprocals (three quadratic steps, six FFMA2: 4.73 instead of 4.53 ms at C4 in the per-pair loop).  Valid for normal
 // positive x below 2^126.
-#ifndef ARVAE_NR_OPS
-#define ARVAE_NR_OPS 5
-#endif
 __device__ __forceinline__ f2_t rcp_newton2(f2_t x) {
     float x0, x1;
     unpack2(x, x0, x1);
     f2_t y = pack2(__int_as_float(0x7EF311C7 - __float_as_int(x0)), __int_as_float(0x7EF311C7 - __float_as_int(x1)));
     const f2_t one = pack2(1.0f, 1.0f), nx = pack2(-x0, -x1);
-#if ARVAE_NR_OPS == 5
     f2_t e = fma2(nx, y, one);
     y = fma2(y, e, y);
     e = fma2(nx, y, one);
     const f2_t t = fma2(e, e, e);
     return fma2(y, t, y);
-#else
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const f2_t e = fma2(nx, y, one);
-        y = fma2(y, e, y);
-    }
-    return y;
-#endif
+}
+// Two reciprocals: on the XU pipe (two MUFU.RCP) or, where a compile-time mask says so, on the FMA pipe.
+template <bool NEWTON>
+__device__ __forceinline__ f2_t rcp2(f2_t x) {
+    if (NEWTON) return rcp_newton2(x);
+    float x0, x1;
+    unpack2(x, x0, x1);
+    return pack2(rcp_approx(x0), rcp_approx(x1));
 }
 
-// Form of the one-MUFU constant-sign loop:
-//   0   r = E_j / (E_i + E_j):          FADD2, two RCP, FMUL2, then the two accumulations     (4 FP32 per two pairs)
-//   1   q = 1 - r = 1 / (1 + E_j F_i):  FFMA2, two RCP, then the two accumulations            (3 FP32 per two pairs)
-//       with F_i = 2^-u_i held per row.  r - r^2 = q - q^2, so the gradient sums are the same expression and only the
-//       two loss expressions swap; 1 + E_j F_i <= 1 + 2^124 for inliers (|u| <= 62).
-// ARVAE_NR_MASK: which of the 16 (column group g, row k, column pair h) slots (bit 8 g + 2 k + h) of a 4 x 8 pair group
-// take their two reciprocals from rcp_newton2 instead of two MUFU.RCP.  ptxas's schedule decides, not the count alone:
-// pair kernel on C4, ms --
-//   form 0 (6-op Newton): no slot 5.86 (scalar loop), 2 of 16 5.48, 4 of 16 (0xC0C0) 5.15, 6 of 16 5.51
-//   form 1, 6-op Newton:  0xC0C0 4.73, 0xC0E0 5.28, 0xE0E0 5.06
-//   form 1, 5-op Newton:  0xE0E0 4.53 (kept), 0xD0D0 4.54, 0xA0E0 4.55, 0x00FC 4.60, 0xA8A8 4.62, 0xE00E 4.65, 0x3838 4.67,
-//                         0xB0B0 4.67, 0x0E0E 4.68, 0xE0E1 4.68, 0x5454 4.71, 0x8383 4.74, 0x0707 4.75, 0x7070 4.77,
-//                         0xE0F0 4.80, 0xC1C1 4.87, 0xE8E0 4.88, 0xC0E0 5.00, 0xE0C0 5.07; unrolling the group loop twice: same
-#ifndef ARVAE_PAIR_FORM
-#define ARVAE_PAIR_FORM 1
-#endif
+// Compile-time choices of the one-MUFU constant-sign loops.  ptxas's schedule decides as much as the instruction counts,
+// so each was an A/B sweep on the GPU (bench_tools/pair_variants.sh, profiles/r2c_pair_ab_variants.jsonl), pair kernel at
+// C4 in ms:
+//  * ARVAE_NR_MASK -- per-pair loop: which of the 16 (column group g, row k, column pair h) slots (bit 8 g + 2 k + h) of a
+//    4 x 8 pair group take the Newton reciprocal: 0xE0E0 4.53 (kept), 0xD0D0 4.54, 0xA0E0 4.55, 0x00FC 4.60, 0xA8A8 4.62,
+//    0xE00E 4.65, 0x3838 4.67, 0x0E0E 4.68, 0x5454 4.71, 0x8383 4.74, 0x7070 4.77, 0xE0F0 4.80, 0xC0E0 5.00, 0xE0C0 5.07
+//    (the round's earlier form r = E_j / (E_i + E_j) with one more FMUL2 per two pairs: 5.15 at its best mask)
+//  * ARVAE_NR_MASK_TP -- shared-reciprocal loop: which of the 8 (column group g, row k) quads (bit 4 g + k): none 3.51;
+//    one quad 0x10 3.214 (kept), 0x20 3.218, 0x02 3.225, 0x01 3.229, 0x40 3.231, 0x04 3.252, 0x80 3.53, 0x08 3.54;
+//    two quads 3.31-3.39.  (Both quotients of a quad instead of their sums: 4.09; the sums without staged T, P: 3.57)
+//  * ARVAE_CONST_OUTER_UNROLL -- pair groups per branch: 1 3.90, 2 3.73, 4 3.62, 8 3.57, 16 3.61, 32 3.87 (sums-only form)
 #ifndef ARVAE_NR_MASK
-#if ARVAE_PAIR_FORM == 1
 #define ARVAE_NR_MASK 0xE0E0
-#else
-#define ARVAE_NR_MASK 0xC0C0
 #endif
-#endif
-// ARVAE_SHARE_MASK: which of the 8 (column group g, row k) quads (bit 4 g + k) of the pair group use the shared-reciprocal
-// form in the build for inner-range data (ONLY1); the others keep the plain form (with ARVAE_NR_MASK_SHARED).
-#ifndef ARVAE_ONLY1_SHARED
-#define ARVAE_ONLY1_SHARED 1
-#endif
-#ifndef ARVAE_SHARE_MASK
-#define ARVAE_SHARE_MASK 0xFF
-#endif
-#ifndef ARVAE_SHARE_FORM
-#define ARVAE_SHARE_FORM 3   // 1: both quotients of a quad (9 packed FP32 per four pairs), 2: their sums only (8; needs mask 0xFF),
-                             // 3: the sums from staged column-pair sums and products (6; needs mask 0xFF)
-#endif
-static_assert(ARVAE_SHARE_FORM < 2 || ARVAE_SHARE_MASK == 0xFF, "the sums-only forms need every quad in the shared form");
 #ifndef ARVAE_NR_MASK_TP
-#define ARVAE_NR_MASK_TP 0x10   // form 3: which of the 8 (column group g, row k) quads (bit 4 g + k) take the packed Newton reciprocal.
-                                // Pair kernel at C4, ms: none 3.51; one quad 3.21-3.25 (0x10 3.214, 0x20 3.218, 0x02 3.225, 0x01 3.229,
-                                // 0x40 3.231, 0x04 3.252; 0x08 3.54, 0x80 3.53); two quads 3.31-3.39; form 2 (no staged sums) 3.57
-#endif
-constexpr bool kStageTP = ARVAE_ONLY1_SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM == 3;
-#ifndef ARVAE_NR_MASK_SHARED
-#define ARVAE_NR_MASK_SHARED 0x0000
+#define ARVAE_NR_MASK_TP 0x10
 #endif
 #ifndef ARVAE_CONST_OUTER_UNROLL
-#define ARVAE_CONST_OUTER_UNROLL 8   // iterations of the 4 x 8 pair-group loop per branch: 1 3.90, 2 3.73, 4 3.62, 8 3.57, 16 3.61, 32 3.87 ms at C4
+#define ARVAE_CONST_OUTER_UNROLL 8
 #endif
 constexpr int kConstOuterUnroll = ARVAE_CONST_OUTER_UNROLL;
 
@@ -268,14 +236,77 @@ __device__ __forceinline__ float pair_r(float ei, float ej, float d, float cabs)
     return rcp_approx(ex2_approx(d * cabs) + 1.0f);       // 1 / (1 + 2^(|c| (xs_i - xs_j)))
 }
 
-// Constant-sign tile: per pair only q = 1 - r = 1 / (1 + E_j F_i), sum q and sum q^2.  The one-MUFU form works on column
-// PAIRS with the packed FP32 instructions: per two pairs FFMA2 (1 + E_j F_i), two MUFU.RCP (or, on 6 of 16 slots, the packed
-// Newton reciprocal on the FMA pipe), FADD2 (sum q), FFMA2 (sum q^2).  SASS of the loop: 118 instructions per 32 pairs
-// (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128): XU pipe 160 and FP32 pipe 156 clk per warp iteration.
-template <bool MUFU1, bool GRAD, bool SHARED = false>
+// Constant-sign tile: only S1 = sum_j q and S2 = sum_j q^2 per row are needed, q = 1 - r = 1 / (1 + E_j F_i) with
+// F_i = 2^-u_i held per row (r - r^2 = q - q^2, so against sums of r only the two loss expressions swap):
+//   s = +1:  sum |t - s| = 2 (n - S1),  sum g / 4 = S2 - S1;      s = -1:  2 S1,  S1 - S2.
+// Both one-MUFU loops work on column PAIRS with the packed FP32 instructions.
+// SHARED: A2[k][1] holds sum 1 / (a b) of the shared-reciprocal loop, S2 = sum w^2 - 2 sum 1 / (a b).
+template <bool GRAD, bool SHARED>
+__device__ __forceinline__ void const_tile_epilogue(const f2_t (&A1)[kTileRI][2], const f2_t (&A2)[kTileRI][2], bool positive,
+                                                    acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k) {
+        float a0, a1, a2, a3, b0, b1, b2, b3;
+        unpack2(A1[k][0], a0, a1);
+        unpack2(A1[k][1], a2, a3);
+        unpack2(A2[k][0], b0, b1);
+        unpack2(A2[k][1], b2, b3);
+        const float S1 = (a0 + a1) + (a2 + a3);
+        const float S2 = SHARED ? fmaf(-2.0f, b2 + b3, b0 + b1) : (b0 + b1) + (b2 + b3);
+        acc_add(dl[k], positive ? 2.0f * ((float)kSubCols - S1) : 2.0f * S1);
+        if (GRAD) acc_add(dg[k], positive ? S2 - S1 : S1 - S2);
+    }
+}
+
+// Shared-reciprocal loop (the build for the common case: every |u| <= kSharedMaxAbsU, so a b <= (1 + 2^62)^2 is finite).
+// A quad = one row x the column pairs (j, j+2) and (j+1, j+3) of a group of four columns shares ONE reciprocal per packed
+// lane, and only the quad's sums are formed:
+//   a = 1 + E_a F_i, b = 1 + E_b F_i;  a + b - 1 = 1 + T F_i,  a b = (a + b - 1) + P F_i^2   with the STAGED column-pair
+//   sums T = E_a + E_b and products P = E_a E_b;  w = q_a + q_b = (a + b) / (a b),  q_a^2 + q_b^2 = w^2 - 2 / (a b).
+// Per quad: three FFMA2 (a + b - 1, a b, w), two MUFU.RCP, FADD2 (sum w), FFMA2 (sum w^2), FADD2 (sum 1/(a b)); one quad
+// of eight takes the Newton reciprocal.  SASS: 580 instructions per 256 pairs (112 MUFU.RCP, 296 FFMA2, 128 FADD2,
+// 17 IADD3, 16 LDS.128): XU pipe 112 and FP32 pipe 106 clk per 32 pairs and warp.
+template <bool GRAD>
+__device__ __forceinline__ void loop_const_shared(const RowRegs &R, const float *__restrict__ stp, bool positive,
+                                                  acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
+    f2_t A1[kTileRI][2], A2[kTileRI][2];  // [k][0]: sum w, sum w^2;  A2[k][1]: sum 1 / (a b);  A1[k][1] stays 0
+#pragma unroll
+    for (int k = 0; k < kTileRI; ++k)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) A1[k][h] = A2[k][h] = pack2(0.0f, 0.0f);
+    const f2_t one = pack2(1.0f, 1.0f);
+#pragma unroll kConstOuterUnroll
+    for (int q = 0; q < kSubCols; q += 8) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const float4 tp = *reinterpret_cast<const float4 *>(stp + q + 4 * g);
+            const f2_t T = pack2(tp.x, tp.y), P = pack2(tp.z, tp.w);
+#pragma unroll
+            for (int k = 0; k < kTileRI; ++k) {
+                const f2_t fk = pack2(R.f[k], R.f[k]), fk2 = pack2(R.f2[k], R.f2[k]);
+                const f2_t tm1 = fma2(T, fk, one);
+                const f2_t p = fma2(P, fk2, tm1);
+                const f2_t rp = ((ARVAE_NR_MASK_TP >> (g * 4 + k)) & 1) ? rcp2<true>(p) : rcp2<false>(p);
+                const f2_t w = fma2(rp, tm1, rp);
+                A1[k][0] = add2(A1[k][0], w);
+                if (GRAD) {
+                    A2[k][0] = fma2(w, w, A2[k][0]);
+                    A2[k][1] = add2(A2[k][1], rp);
+                }
+            }
+        }
+    }
+    const_tile_epilogue<GRAD, true>(A1, A2, positive, dl, dg);
+}
+
+// Per-pair loops.  One-MUFU form (complete build: valid for |u| <= 62, i.e. 1 + E_j F_i <= 1 + 2^124): per two pairs
+// FFMA2 (1 + E_j F_i), two MUFU.RCP (on 6 of 16 slots the Newton reciprocal), FADD2 (sum q), FFMA2 (sum q^2) -- SASS: 118
+// instructions per 32 pairs (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128).  Two-MUFU form (tiles touching the
+// outlier segment): EX2 + RCP on the scaled latent difference.
+template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,
                                            const float *__restrict__ sx, float cabs, bool positive,
-                                           acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], const float *__restrict__ stp = nullptr) {
+                                           acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI]) {
     if (MUFU1) {
         f2_t A1[kTileRI][2], A2[kTileRI][2];
 #pragma unroll
@@ -287,102 +318,22 @@ __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__rest
         for (int q = 0; q < kSubCols; q += 8) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                if (SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM == 3) {
-                    // The quad (columns j, j+2 and j+1, j+3 of a group of four, row i) from the STAGED column-pair sums
-                    // T = E_a + E_b and products P = E_a E_b:  a + b - 1 = 1 + T F_i,  a b = (a + b - 1) + P F_i^2,
-                    // w = q_a + q_b = (a + b) / (a b) -- three FFMA2 where the per-pair form needs five packed operations.
-                    const float4 tp = *reinterpret_cast<const float4 *>(stp + q + 4 * g);
-                    const f2_t T = pack2(tp.x, tp.y), P = pack2(tp.z, tp.w);
-#pragma unroll
-                    for (int k = 0; k < kTileRI; ++k) {
-                        const f2_t fk = pack2(R.f[k], R.f[k]), fk2 = pack2(R.f2[k], R.f2[k]);
-                        const f2_t tm1 = fma2(T, fk, one);
-                        const f2_t p = fma2(P, fk2, tm1);
-                        f2_t rp;
-                        if ((ARVAE_NR_MASK_TP >> (g * 4 + k)) & 1) {
-                            rp = rcp_newton2(p);
-                        } else {
-                            float p0, p1;
-                            unpack2(p, p0, p1);
-                            rp = pack2(rcp_approx(p0), rcp_approx(p1));
-                        }
-                        const f2_t w = fma2(rp, tm1, rp);
-                        A1[k][0] = add2(A1[k][0], w);
-                        if (GRAD) {
-                            A2[k][0] = fma2(w, w, A2[k][0]);
-                            A2[k][1] = add2(A2[k][1], rp);
-                        }
-                    }
-                    continue;
-                }
                 const float4 vj = *reinterpret_cast<const float4 *>(se + q + 4 * g);
                 const f2_t vv[2] = {pack2(vj.x, vj.y), pack2(vj.z, vj.w)};
 #pragma unroll
                 for (int k = 0; k < kTileRI; ++k) {
-                    const f2_t ri = ARVAE_PAIR_FORM == 1 ? pack2(R.f[k], R.f[k]) : pack2(R.e[k], R.e[k]);
-                    if (SHARED && ARVAE_PAIR_FORM == 1 && ((ARVAE_SHARE_MASK >> (g * 4 + k)) & 1)) {
-                        // two column pairs share their reciprocals: 1/a = b / (a b), 1/b = a / (a b) -- three FMUL2 and two
-                        // MUFU.RCP for four pairs instead of four MUFU.RCP.  a b <= (1 + 2^62)^2: the caller guarantees
-                        // |u| <= kSharedMaxAbsU for every element
-                        const f2_t sa = fma2(vv[0], ri, one), sb = fma2(vv[1], ri, one);
-                        float p0, p1;
-                        unpack2(mul2(sa, sb), p0, p1);
-                        const f2_t rp = pack2(rcp_approx(p0), rcp_approx(p1));
-                        if (ARVAE_SHARE_FORM == 2) {
-                            // sums of the quad without the two quotients: q_a + q_b = (a + b) / (a b) =: w, and
-                            // q_a^2 + q_b^2 = w^2 - 2 q_a q_b = w^2 - 2 / (a b): accumulate w, w^2 and 1 / (a b)
-                            const f2_t w = mul2(rp, add2(sa, sb));
-                            A1[k][0] = add2(A1[k][0], w);
-                            if (GRAD) {
-                                A2[k][0] = fma2(w, w, A2[k][0]);
-                                A2[k][1] = add2(A2[k][1], rp);
-                            }
-                            continue;
-                        }
-                        const f2_t qa = mul2(rp, sb), qb = mul2(rp, sa);
-                        A1[k][0] = add2(A1[k][0], qa);
-                        A1[k][1] = add2(A1[k][1], qb);
-                        if (GRAD) {
-                            A2[k][0] = fma2(qa, qa, A2[k][0]);
-                            A2[k][1] = fma2(qb, qb, A2[k][1]);
-                        }
-                        continue;
-                    }
+                    const f2_t fk = pack2(R.f[k], R.f[k]);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        // form 0: E_i + E_j;  form 1: 1 + E_j F_i = (E_i + E_j) / E_i
-                        const f2_t sum = ARVAE_PAIR_FORM == 1 ? fma2(vv[h], ri, one) : add2(ri, vv[h]);
-                        f2_t rq;
-                        if (((SHARED ? ARVAE_NR_MASK_SHARED : ARVAE_NR_MASK) >> (g * 8 + k * 2 + h)) & 1) {  // compile-time: a fixed subset of the 16 slots
-                            rq = rcp_newton2(sum);
-                        } else {
-                            float s0, s1;
-                            unpack2(sum, s0, s1);
-                            rq = pack2(rcp_approx(s0), rcp_approx(s1));
-                        }
-                        const f2_t r = ARVAE_PAIR_FORM == 1 ? rq : mul2(rq, vv[h]);  // form 0: r;  form 1: 1 - r
-                        A1[k][h] = add2(A1[k][h], r);
-                        if (GRAD) A2[k][h] = fma2(r, r, A2[k][h]);
+                        const f2_t sum = fma2(vv[h], fk, one);  // 1 + E_j F_i = (E_i + E_j) / E_i
+                        const f2_t qq = ((ARVAE_NR_MASK >> (g * 8 + k * 2 + h)) & 1) ? rcp2<true>(sum) : rcp2<false>(sum);
+                        A1[k][h] = add2(A1[k][h], qq);
+                        if (GRAD) A2[k][h] = fma2(qq, qq, A2[k][h]);
                     }
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < kTileRI; ++k) {
-            float a0, a1, a2, a3, b0, b1, b2, b3;
-            unpack2(A1[k][0], a0, a1);
-            unpack2(A1[k][1], a2, a3);
-            unpack2(A2[k][0], b0, b1);
-            unpack2(A2[k][1], b2, b3);
-            const float S1 = (a0 + a1) + (a2 + a3);
-            const float S2 = (SHARED && ARVAE_PAIR_FORM == 1 && ARVAE_SHARE_FORM >= 2) ? fmaf(-2.0f, b2 + b3, b0 + b1)
-                                                                                       : (b0 + b1) + (b2 + b3);
-            // s=+1: sum|t-s| = 2 S1, sum g/4 = -(S1-S2);  s=-1: 2 (n - S1), +(S1-S2).  Form 1 sums q = 1 - r: sum r = n - S1,
-            // and r - r^2 = q - q^2, so only the loss expressions swap
-            const bool small_side = ARVAE_PAIR_FORM == 1 ? !positive : positive;
-            acc_add(dl[k], small_side ? 2.0f * S1 : 2.0f * ((float)kSubCols - S1));
-            if (GRAD) acc_add(dg[k], positive ? S2 - S1 : S1 - S2);
-        }
+        const_tile_epilogue<GRAD, false>(A1, A2, positive, dl, dg);
         return;
     }
     float A1[kTileRI][4], A2[kTileRI][4];
@@ -795,14 +746,16 @@ __device__ __forceinline__ void sweep_subchunk(int cls, const RowRegs &R, const 
                                                const float *sx, const float *sa, float cabs,
                                                acc_t (&dl)[kTileRI], acc_t (&dg)[kTileRI], int (&ds)[kTileRI],
                                                const float *stp = nullptr) {
-    if (cls == kClassPos) {
-        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, true, dl, dg, stp);
+    if (cls == kClassPos) {  // (two call sites on purpose: one copy of the loop per sign, as measured)
+        if (MUFU1 && SHARED) loop_const_shared<GRAD>(R, stp, true, dl, dg);
+        else loop_const<MUFU1, GRAD>(R, se, sx, cabs, true, dl, dg);
         if (SIGNS) {
 #pragma unroll
             for (int k = 0; k < kTileRI; ++k) ds[k] += kSubCols;
         }
     } else if (cls == kClassNeg) {
-        loop_const<MUFU1, GRAD, SHARED>(R, se, sx, cabs, false, dl, dg, stp);
+        if (MUFU1 && SHARED) loop_const_shared<GRAD>(R, stp, false, dl, dg);
+        else loop_const<MUFU1, GRAD>(R, se, sx, cabs, false, dl, dg);
         if (SIGNS) {
 #pragma unroll
             for (int k = 0; k < kTileRI; ++k) ds[k] -= kSubCols;
@@ -971,7 +924,7 @@ reg_tiles_kernel(TilesArgs a) {
             const int64_t col = (((int64_t)(sp + w) * a.P) % a.S) * kSubCols + (q - w * kSubCols);
             const float4 e4 = *reinterpret_cast<const float4 *>(Er + col);
             *reinterpret_cast<float4 *>(hse + q) = e4;
-            if (ONLY1 && kStageTP)  // per group of four columns: sums and products of the column pairs (j, j+2), (j+1, j+3)
+            if (ONLY1)  // per group of four columns: sums and products of the column pairs (j, j+2), (j+1, j+3)
                 *reinterpret_cast<float4 *>(hstp + q) = make_float4(e4.x + e4.z, e4.y + e4.w, e4.x * e4.z, e4.y * e4.w);
             *reinterpret_cast<float4 *>(hsx + q) = *reinterpret_cast<const float4 *>(Xr + col);
             *reinterpret_cast<float4 *>(hsa + q) = *reinterpret_cast<const float4 *>(Ar + col);
@@ -983,7 +936,7 @@ reg_tiles_kernel(TilesArgs a) {
                 const unsigned int word = a.cls8[rr * a.S + sp + w];
                 const int cls = (word >> (2 * warp)) & 3;        // planned class of this warp's tile
                 const bool mufu1 = ONLY1 || ((word >> (16 + warp)) & 1u) == 0u;  // planned tanh form
-                if (mufu1) sweep_subchunk<true, GRAD, SIGNS, ONLY1 && ARVAE_ONLY1_SHARED>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds, hstp + sub);
+                if (mufu1) sweep_subchunk<true, GRAD, SIGNS, ONLY1>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds, hstp + sub);
                 else sweep_subchunk<false, GRAD, SIGNS>(cls, R, hse + sub, hsx + sub, hsa + sub, a.cabs, dl, dg, ds);
             }
         }

@@ -7,9 +7,9 @@
 #   bash bench_tools/pair_variants.sh build  name1 "-DARVAE_NR_MASK_TP=0x10" name2 "-DARVAE_NR_MASK_TP=0x01 -DARVAE_CONST_OUTER_UNROLL=4" ...
 #   bash bench_tools/pair_variants.sh run    [pair_ab.py environment, e.g. AB_WORKLOAD=c2_dsprites_b4096 AB_BATCH=65536]
 #
-# Macros (csrc/reg_sorted.cu): ARVAE_PAIR_FORM 0|1, ARVAE_NR_OPS 5|6, ARVAE_NR_MASK (16 bits, per-pair form),
-# ARVAE_ONLY1_SHARED 0|1, ARVAE_SHARE_FORM 1|2|3, ARVAE_SHARE_MASK (8 bits, form 1), ARVAE_NR_MASK_TP (8 bits, form 3),
-# ARVAE_CONST_OUTER_UNROLL, ARVAE_COST_GENERAL1, ARVAE_COST_TIE1.
+# Macros (csrc/reg_sorted.cu): ARVAE_NR_MASK (16 bits, per-pair loop), ARVAE_NR_MASK_TP (8 bits, shared-reciprocal loop),
+# ARVAE_CONST_OUTER_UNROLL, ARVAE_COST_GENERAL1, ARVAE_COST_TIE1.  (The forms that lost -- r = E_j / (E_i + E_j), both
+# quotients of a quad, sums without staged T and P, the six-instruction Newton step -- are in the history of that file.)
 # The variant libraries go to bench_tools/_exp/ (git-ignored; they travel to the GPU box with the snapshot).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
