@@ -1,31 +1,33 @@
 // reg_sorted.cu -- attribute-sorted pair kernel (sm_100a): the fast path for large batches.
 //
-// Same arithmetic as reg_dense.cu (reference utils/trainer.py:390-401 and its autograd backward),
-// reorganised so that almost every pair costs 0.63 MUFU + 2.4 packed FP32 instructions instead of 2 + 12:
+// Same arithmetic as reg_dense.cu (reference utils/trainer.py:390-401 and its autograd backward), reorganised so that
+// almost every pair costs 0.44 MUFU + 1.7 packed FP32 instructions instead of 2 MUFU + 12 scalar ones:
 //
-//  * rows and columns of each regularised dim are ordered by attribute value (sort.cu).  A tile of
-//    128 rows (one warp) x 256 columns whose attribute ranges do not overlap has a CONSTANT sign s_ij, so per
-//    pair only sum(r) and sum(r^2) are needed, r = (1 - t)/2:
+//  * rows and columns of each regularised dim are ordered by attribute value (sort.cu).  A tile of 128 rows (one warp)
+//    x 256 columns whose attribute ranges do not overlap has a CONSTANT sign s_ij, so per pair only sum(r) and sum(r^2)
+//    are needed, r = (1 - t)/2:
 //        s = +1:  |t - s| = 2r        g = -(1 - t^2) = -4 (r - r^2)
 //        s = -1:  |t - s| = 2(1 - r)  g = +4 (r - r^2)
-//    Tiles inside one tie group (all attributes equal, incl. NaN rows/columns: NaN ties with
-//    everything) have s = 0:  |t| = 2 |1/2 - r|, g = sgn(1/2 - r) 4 (r - r^2).  Only tiles that
-//    straddle the diagonal band / a tie-group edge run the general loop with per-pair float
-//    compares of the raw attributes -- the sign is exact by construction in all three classes.
-//  * r = 1/(1 + 2^(u_i-u_j)) = E_j / (E_i + E_j) with u = 2 f log2(e) x and E = 2^u precomputed once
-//    per element: one MUFU.RCP per pair (the constant-sign loop evaluates 1 - r = 1 / (1 + E_j F_i), F_i = 2^-u_i per row).  Safe while |u| <= 62 for every element of the dim (no
-//    overflow in E_i+E_j, full relative accuracy in both saturation directions); a per-dim flag
-//    computed by the gather kernel falls back to the 2-MUFU form (EX2 + RCP on the scaled latent
-//    difference) otherwise.
-//  * wherever a pair can be a tie (tie and general tiles), sgn(t) is taken from the exact float
-//    difference xs_i - xs_j of the (sign-adjusted) latents, never from the approximated tanh: near
-//    t = 0 the factor (1 - t^2) is maximal and abs-backward's sgn(0) = 0 must hold exactly for
-//    equal latents (the diagonal, duplicated samples).
-//  * work is cut into units (1024-row tile, 256-column sub-chunk), visited in a permuted column order;
-//    a planner kernel models each unit's cost and every CTA of a persistent grid (one per SM) gets a
-//    cost-balanced contiguous range, which its two 8-warp halves consume from both ends (dynamic
-//    meeting point), so there is no wave tail and no idle half; row partials are fixed-point integers
-//    written to a (segment, half, row tile) slot: the result does not depend on the split.
+//    Tiles inside one tie group (all attributes equal, incl. NaN rows/columns: NaN ties with everything) have s = 0:
+//    |t| = 2 |1/2 - r|, g = sgn(1/2 - r) 4 (r - r^2).  Only tiles that straddle the diagonal band / a tie-group edge run
+//    the general loop with per-pair float compares of the raw attributes -- the sign is exact by construction in all
+//    three classes.
+//  * r = 1/(1 + 2^(u_i-u_j)) = E_j / (E_i + E_j) with u = 2 f log2(e) x and E = 2^u precomputed once per element: one
+//    MUFU.RCP per pair, safe while |u| <= 62 (no overflow, full relative accuracy in both saturation directions).
+//    Samples beyond that carry an outlier bit in their sort key and form a segment of their own: only tiles touching it
+//    take the 2-MUFU form (EX2 + RCP on the scaled latent difference).
+//  * constant-sign tiles go further (loop_const_shared): with q = 1 - r = 1 / (1 + E_j F_i), F_i = 2^-u_i, two pairs share
+//    ONE reciprocal 1 / (a b) and only the sums q_a + q_b, q_a^2 + q_b^2 are formed, from column-pair sums and products
+//    staged in shared memory -- valid while |u| <= 31 for EVERY element of the call, which a device flag decides: the
+//    build of the kernel for that case (ONLY1) or the complete one (per-pair reciprocals) does the work.
+//  * wherever a pair can be a tie (tie and general tiles), sgn(t) is taken from the exact float difference xs_i - xs_j
+//    of the (sign-adjusted) latents, never from the approximated tanh: near t = 0 the factor (1 - t^2) is maximal and
+//    abs-backward's sgn(0) = 0 must hold exactly for equal latents (the diagonal, duplicated samples).
+//  * work is cut into units (1024-row tile, 256-column sub-chunk), visited in a permuted column order; a planner kernel
+//    models each unit's cost and every CTA of a persistent grid (one per SM) gets a cost-balanced contiguous range, which
+//    its two 8-warp halves consume from both ends (dynamic meeting point), so there is no wave tail and no idle half;
+//    row partials are fixed-point integers added to per-row accumulators with integer atomics: the result does not
+//    depend on the split.
 #include <stdlib.h>
 #include <string.h>
 
