@@ -302,8 +302,8 @@ __device__ __forceinline__ void loop_const_shared(const RowRegs &R, const float 
 }
 
 // Per-pair loops.  One-MUFU form (complete build: valid for |u| <= 62, i.e. 1 + E_j F_i <= 1 + 2^124): per two pairs
-// FFMA2 (1 + E_j F_i), two MUFU.RCP (on 6 of 16 slots the Newton reciprocal), FADD2 (sum q), FFMA2 (sum q^2) -- SASS: 118
-// instructions per 32 pairs (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128).  Two-MUFU form (tiles touching the
+// FFMA2 (1 + E_j F_i), two MUFU.RCP (on 6 of 16 slots the Newton reciprocal), FADD2 (sum q), FFMA2 (sum q^2) -- SASS: 914
+// instructions per 256 pairs (160 MUFU.RCP, 496 FFMA2, 128 FADD2, 97 IADD3, 16 LDS.128).  Two-MUFU form (tiles touching the
 // outlier segment): EX2 + RCP on the scaled latent difference.
 template <bool MUFU1, bool GRAD>
 __device__ __forceinline__ void loop_const(const RowRegs &R, const float *__restrict__ se,

@@ -50,16 +50,17 @@ MUFU_LANES_PER_CLK_SM = 16.0     # sm_100 MUFU issue rate; confirmed by bench_to
 #    instructions per 256 pairs: 112 MUFU.RCP, 296 FFMA2, 128 FADD2 (two FP32 operations each), 17 IADD3, 16 LDS.128,
 #    11 others;
 #  * complete build (outliers or latents beyond that range present): q = 1 / (1 + E_j F_i) per pair, 6 of the 16 slots of a
-#    4 x 8 pair group take their reciprocals from a packed Newton iteration on the FMA pipe -- 118 instructions per
-#    32 pairs: 20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3, 2 LDS.128, 6 others.
+#    4 x 8 pair group take their reciprocals from a packed Newton iteration on the FMA pipe -- 914 instructions per
+#    256 pairs: 160 MUFU.RCP, 496 FFMA2, 128 FADD2, 97 IADD3, 16 LDS.128, 17 others.
+# tests/test_bench_contract.py holds these counts against cuobjdump -sass of the built library.
 # Used for the roofs of the ACTUAL mix.
 SHARED_MAX_ABS_U = 31.0
 SHARED_LOOP = {"mufu_per_inlier_pair": 112.0 / 256.0, "instr_per_pair": 580.0 / 256.0, "fp32_ops_per_pair": (296 + 128) * 2 / 256.0,
                "sass": "580 instructions per 256 pairs (112 MUFU.RCP, 296 FFMA2, 128 FADD2, 17 IADD3, 16 LDS.128)",
                "what": "shared-reciprocal build (every |u| <= 31): one reciprocal per two pairs from staged column-pair sums and "
                        "products, 1 of 8 quads on packed Newton reciprocals"}
-PLAIN_LOOP = {"mufu_per_inlier_pair": 20.0 / 32.0, "instr_per_pair": 118.0 / 32.0, "fp32_ops_per_pair": (62 + 16) * 2 / 32.0,
-              "sass": "118 instructions per 32 pairs (20 MUFU.RCP, 62 FFMA2, 16 FADD2, 12 IADD3)",
+PLAIN_LOOP = {"mufu_per_inlier_pair": 160.0 / 256.0, "instr_per_pair": 914.0 / 256.0, "fp32_ops_per_pair": (496 + 128) * 2 / 256.0,
+              "sass": "914 instructions per 256 pairs (160 MUFU.RCP, 496 FFMA2, 128 FADD2, 97 IADD3, 16 LDS.128)",
               "what": "complete build: 6 of 16 slots per pair group take packed Newton reciprocals on the FMA pipe"}
 ISSUE_LANES_PER_CLK_SM = 128.0   # 4 schedulers x 32 lanes
 FP32_LANES_PER_CLK_SM = 128.0    # FMA pipe (FFMA2 / FADD2 / FMUL2 measured at 123 FP32 operations/clk/SM, profiles/r2_pipe_rates.json)
