@@ -91,7 +91,7 @@ int run_sign_matrix(const float *a, int64_t stride, int64_t B, int8_t *out, cuda
 // [32] plan error, [33] some element of some dim is an outlier or outside the shared-reciprocal range (|u| > 31), [34] "last CTA" ticket of the plan kernel,
 // [35, 67) per-dim non-finite latent bits (1: +-inf present, 2: NaN present), [67, 99) n_in per dim.
 constexpr int kFlagError = ARVAE_MAX_REG_DIMS;
-constexpr int kFlagAnyTwoMufu = ARVAE_MAX_REG_DIMS + 1;
+constexpr int kFlagNeedComplete = ARVAE_MAX_REG_DIMS + 1;
 constexpr int kFlagTicket = ARVAE_MAX_REG_DIMS + 2;
 constexpr int kFlagNonFinite = ARVAE_MAX_REG_DIMS + 3;
 constexpr int kFlagNIn = 2 * ARVAE_MAX_REG_DIMS + 3;
@@ -112,7 +112,7 @@ struct KeySpec {
 constexpr float kMufu1MaxAbsU = 62.0f;
 // The pair kernel's build for the common case (reg_sorted.cu: ONLY1) shares one reciprocal between two pairs, 1 / (a b) with
 // a, b <= 1 + 2^(2 kSharedMaxAbsU): it runs only when every element of every dim is within this range (flag
-// kFlagAnyTwoMufu stays 0), the complete build otherwise.
+// kFlagNeedComplete stays 0), the complete build otherwise.
 constexpr float kSharedMaxAbsU = 31.0f;
 constexpr unsigned long long kKeyIdxMask = 0x7FFFFFFFull;  // segmented keys: low 31 bits = sample index
 __host__ __device__ static inline bool key_is_outlier(unsigned long long k) { return (k >> 63) != 0; }

@@ -214,7 +214,7 @@ __device__ __forceinline__ void place_run_elem(const uint4 &e, int64_t pos, int6
     Es[base + pos] = key_is_outlier(key) ? 1.0f : exp2f(cabs * xs);
     perm[base + pos] = (int)(key & kKeyIdxMask);
     note_nonfinite(xs, flags, r);
-    if (key_is_outlier(key) || !(fabsf(cabs * xs) <= kSharedMaxAbsU)) atomicOr(flags + kFlagAnyTwoMufu, 1);
+    if (key_is_outlier(key) || !(fabsf(cabs * xs) <= kSharedMaxAbsU)) atomicOr(flags + kFlagNeedComplete, 1);
 }
 
 // One CTA per 256 consecutive elements of one run (and dim).  Their keys ascend, so inside any other run only the

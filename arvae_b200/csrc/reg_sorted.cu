@@ -108,7 +108,7 @@ sorted_gather_kernel(const unsigned long long *__restrict__ keys, int64_t N,
         perm[o] = (int)idx;
         // unsegmented keys (triangle mode): one out-of-range element sends the whole dim to the two-MUFU form
         if (unsegmented && !(fabsf(u) <= kMufu1MaxAbsU)) atomicOr(flags + r, 1);
-        if (!(fabsf(u) <= kSharedMaxAbsU)) atomicOr(flags + kFlagAnyTwoMufu, 1);
+        if (!(fabsf(u) <= kSharedMaxAbsU)) atomicOr(flags + kFlagNeedComplete, 1);
         note_nonfinite(xs, flags, r);
         note_segment_boundary(kr, k, B, flags + kFlagNIn + r);
     } else {  // padding: |t - s| = 1 and zero gradient for every row, in either tanh form
@@ -483,8 +483,9 @@ struct TilesArgs {
     int c_first;                // first of those CTAs this launch runs (0 on a single GPU)
     int64_t n_rr;               // R * n_row_tiles
     int force_general;          // treat every tile as general (unsorted input / debugging)
-    int dual;                   // the launch is a pair of kernels: the one-MUFU-only build runs when no element of any
-                                // dim needs the two-MUFU form (flags[kFlagAnyTwoMufu] == 0), the complete one otherwise
+    int dual;                   // the launch is a pair of kernels: the common-case build (ONLY1) works when every element
+                                // of every dim is within the shared-reciprocal range (flags[kFlagNeedComplete] == 0), the
+                                // complete one otherwise
     // plan (plan_classes_kernel / plan_scan_kernel): per fine unit in VISITING order u = rr * S + s'
     unsigned int *cls8;         // [F] per warp w: 2-bit tile class (bits 2w..2w+1) and tanh form (bit 16+w: 1 = two MUFU)
     unsigned short *cost8;      // [F] modelled cost of the unit (sum over the tile's warps)
@@ -512,7 +513,7 @@ __device__ __forceinline__ long long ceil_share(long long c, long long T, long l
 }
 
 // Modelled cost (relative time) of one warp's 128 x 256 tile by class and tanh form, in units where the one-MUFU
-// constant-sign tile of the build that will run is 8.  The build is known when the plan is made (flag kFlagAnyTwoMufu):
+// constant-sign tile of the build that will run is 8.  The build is known when the plan is made (flag kFlagNeedComplete):
 // the common-case build (ONLY1: shared-reciprocal constant-sign loop, 3.57 ms at C4) or the complete one (plain loop,
 // 4.53 ms).  The warps of a half wait for each other at every grant, so a slow tile costs its half more than its share
 // of the instructions: the constants are fitted, not counted -- pair kernel at B = 65 536 on dSprites-shaped labels
@@ -559,7 +560,7 @@ plan_classes_kernel(TilesArgs a, int *__restrict__ combo_cost, int clear_acc, un
     const float *Ar = a.As + (int64_t)r * a.Bpad;
     const int *rp = a.rowpos ? a.rowpos + (int64_t)r * a.n_rows : nullptr;
     const bool dim_mufu1 = a.flags[r] == 0;
-    const bool shared_build = a.dual && a.flags[kFlagAnyTwoMufu] == 0;  // which build of the pair kernel will work
+    const bool shared_build = a.dual && a.flags[kFlagNeedComplete] == 0;  // which build of the pair kernel will work
     const int64_t nin = a.n_in[r];
     constexpr int kWarpRows = kTileRows / (kTileThreads / 32);
     if (threadIdx.x < kTileThreads / 32) {
@@ -811,7 +812,7 @@ reg_tiles_kernel(TilesArgs a) {
     __shared__ int s_grant[2][2];        // per half: first unit (linear) and count of the current grant
 
     pdl_wait();  // launched ahead of the plan kernel's end (programmatic dependent launch): wait for the plan
-    if (a.dual && (a.flags[kFlagAnyTwoMufu] != 0) == ONLY1) return;  // the other build's turn
+    if (a.dual && (a.flags[kFlagNeedComplete] != 0) == ONLY1) return;  // the other build's turn
     const long long c = (long long)a.c_first + blockIdx.x;
     if (a.dbg_times && threadIdx.x == 0) {
         unsigned long long t;
